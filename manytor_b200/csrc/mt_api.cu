@@ -1,0 +1,843 @@
+// C ABI of manytor_b200 (see include/manytor_b200.h): handle, state in HBM,
+// kernel dispatch and the non-hot helper kernels.  There is deliberately no CPU
+// path here: without a CUDA device every entry point fails with MT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "mt_step.cuh"
+
+using namespace mt;
+
+// ----------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MT_ERR_NO_DEVICE \
+                                                                                     : MT_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ----------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------
+struct mt_env {
+    mt_config cfg;
+    long long n, n_pad, n_tiles;
+    int arm;  // 0 = closed form reference arm, else J (generic chain)
+    float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
+    uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
+    unsigned long long *stats = nullptr;
+    const float *obj_stream = nullptr;
+    int32_t obj_sets = 0;
+    unsigned long long step_index = 0;
+    long long env_steps = 0, launches = 0;
+    bool was_reset = false;
+    StepParams base;
+    // mt_step_host resources
+    static constexpr int kStreams = 4;
+    cudaStream_t hs[kStreams] = {};
+    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+    uint8_t *h_done = nullptr;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+static const float kRefDh[4][4] = {{0.0f, -1.57079632679f, 4.3f, 0.0f},
+                                   {0.0f, 1.57079632679f, 0.0f, 0.0f},
+                                   {0.0f, -1.57079632679f, 24.3f, 0.0f},
+                                   {27.0f, 1.57079632679f, 0.0f, -1.57079632679f}};
+
+static bool is_reference_arm(const mt_config &c) {
+    if (c.n_joints != 4) return false;
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k)
+            if (std::fabs(c.dh[i][k] - kRefDh[i][k]) > 1e-6f) return false;
+    return c.obs_frame == 3 && c.ground_frame_a == 3 && c.ground_frame_b == 4 && c.catch_frame == 4;
+}
+
+static double snap(double v) { return std::fabs(v) < 1e-12 ? 0.0 : (std::fabs(std::fabs(v) - 1.0) < 1e-12 ? (v > 0 ? 1.0 : -1.0) : v); }
+
+extern "C" int mt_abi_version(void) { return MT_ABI_VERSION; }
+extern "C" const char *mt_last_error(void) { return g_err; }
+
+extern "C" int mt_config_init(mt_config *cfg) {
+    if (!cfg) return fail(MT_ERR_INVALID, "cfg is NULL");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(mt_config);
+    cfg->n_envs = 1;
+    cfg->n_joints = 4;
+    cfg->n_obj = 10;
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 4; ++k) cfg->dh[i][k] = kRefDh[i][k];
+    cfg->obs_frame = 3;
+    cfg->ground_frame_a = 3;
+    cfg->ground_frame_b = 4;
+    cfg->catch_frame = 4;
+    cfg->radius = 51.3f;
+    cfg->catch_tol = 8.0f;
+    cfg->substeps = 25;
+    cfg->horizon = 0;
+    cfg->terminate_on_ground = 0;
+    cfg->auto_reset = 0;
+    cfg->obs_after_reset = 0;
+    cfg->fk_mode = 0;
+    cfg->action_low = -180;
+    cfg->action_high = 180;
+    cfg->seed = 0;
+    return MT_OK;
+}
+
+static int validate(const mt_config &c) {
+    if (c.struct_size != sizeof(mt_config)) return fail(MT_ERR_INVALID, "mt_config.struct_size %u != %zu (ABI mismatch)", c.struct_size, sizeof(mt_config));
+    if (c.n_envs < 1) return fail(MT_ERR_INVALID, "n_envs must be >= 1");
+    if (c.n_joints < 2 || c.n_joints > MT_MAX_JOINTS) return fail(MT_ERR_INVALID, "n_joints must be in [2, %d]", MT_MAX_JOINTS);
+    if (c.n_obj < 1 || c.n_obj > MT_MAX_OBJ) return fail(MT_ERR_INVALID, "n_obj must be in [1, %d]", MT_MAX_OBJ);
+    const int J = c.n_joints;
+    const int fr[4] = {c.obs_frame, c.ground_frame_a, c.ground_frame_b, c.catch_frame};
+    for (int f : fr)
+        if (f < 0 || f > J) return fail(MT_ERR_INVALID, "frame selector %d outside [0, %d]", f, J);
+    if (c.substeps < 2 || c.substeps > 4096) return fail(MT_ERR_INVALID, "substeps must be in [2, 4096]");
+    if (c.horizon < 0 || c.horizon > 65535) return fail(MT_ERR_INVALID, "horizon must be in [0, 65535]");
+    if (c.action_high <= c.action_low) return fail(MT_ERR_INVALID, "action_high must exceed action_low");
+    if (!(c.radius > 0.f) || !(c.catch_tol >= 0.f)) return fail(MT_ERR_INVALID, "radius must be > 0 and catch_tol >= 0");
+    if (c.fk_mode < 0 || c.fk_mode > 2) return fail(MT_ERR_INVALID, "fk_mode must be 0, 1 or 2");
+    if (c.fk_mode == 2 && !is_reference_arm(c)) return fail(MT_ERR_INVALID, "fk_mode=2 (closed form) needs the reference DH table and frames");
+    return MT_OK;
+}
+
+static void fill_arm(const mt_config &c, StepParams &P) {
+    const int J = c.n_joints;
+    for (int i = 0; i < MT_MAX_JOINTS; ++i) P.arm[i] = JointConst{0, 0, 1, 0, 1, 0};
+    for (int i = 0; i < J; ++i) {
+        P.arm[i].a = c.dh[i][0];
+        P.arm[i].d = c.dh[i][2];
+        P.arm[i].ca = (float)snap(std::cos((double)c.dh[i][1]));
+        P.arm[i].sa = (float)snap(std::sin((double)c.dh[i][1]));
+        P.arm[i].co = (float)snap(std::cos((double)c.dh[i][3]));
+        P.arm[i].so = (float)snap(std::sin((double)c.dh[i][3]));
+    }
+    // obs anchor at the zero pose (manytor.py:224-225), fp64 chain on the snapped table
+    double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
+    double anchor[3] = {0, 0, 0};
+    for (int i = 0; i < J; ++i) {
+        const double ct = P.arm[i].co, st = P.arm[i].so, ca = P.arm[i].ca, sa = P.arm[i].sa;
+        for (int r = 0; r < 3; ++r) {
+            double u = R[r][0] * ct + R[r][1] * st, v = R[r][1] * ct - R[r][0] * st, r2 = R[r][2];
+            t[r] += P.arm[i].a * u + P.arm[i].d * r2;
+            R[r][0] = u;
+            R[r][1] = v * ca + r2 * sa;
+            R[r][2] = r2 * ca - v * sa;
+        }
+        if (i + 1 == c.obs_frame) { anchor[0] = t[0]; anchor[1] = t[1]; anchor[2] = t[2]; }
+    }
+    for (int k = 0; k < 3; ++k) P.zero_anchor[k] = (float)anchor[k];
+}
+
+static void fill_params(const mt_config &c, StepParams &P) {
+    std::memset(&P, 0, sizeof(P));
+    P.n_obj = c.n_obj;
+    P.n_joints = c.n_joints;
+    P.substeps = c.substeps;
+    P.horizon = c.horizon;
+    P.flags = (c.terminate_on_ground ? kTerminateOnGround : 0) | (c.auto_reset ? kAutoReset : 0) |
+              (c.obs_after_reset ? kObsAfterReset : 0);
+    P.action_low = c.action_low;
+    P.action_span = (uint32_t)(c.action_high - c.action_low);
+    P.radius = c.radius;
+    P.catch_tol = c.catch_tol;
+    P.inv_div = 1.0f / (float)(c.substeps - 1);
+    P.obs_frame = c.obs_frame;
+    P.ground_a = c.ground_frame_a;
+    P.ground_b = c.ground_frame_b;
+    P.catch_frame = c.catch_frame;
+    P.seed_lo = (uint32_t)c.seed;
+    P.seed_hi = (uint32_t)(c.seed >> 32);
+    P.env_id_base = c.env_id_base;
+    P.tile_bytes = (uint32_t)(kTile * 3 * c.n_obj * 4);
+    fill_arm(c, P);
+}
+
+extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
+    if (!cfg || !out) return fail(MT_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    if (int rc = validate(*cfg)) return rc;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return fail(MT_ERR_NO_DEVICE, "no CUDA device (%s); manytor_b200 has no CPU fallback",
+                    ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= count) return fail(MT_ERR_INVALID, "device %d outside [0, %d)", cfg->device, count);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(MT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                    prop.major, prop.minor);
+    DeviceGuard guard(cfg->device);
+    mt_env *e = new (std::nothrow) mt_env();
+    if (!e) return fail(MT_ERR_INVALID, "out of host memory");
+    e->cfg = *cfg;
+    e->n = cfg->n_envs;
+    e->n_tiles = (e->n + kTile - 1) / kTile;
+    e->n_pad = e->n_tiles * kTile;
+    e->arm = (cfg->fk_mode != 1 && is_reference_arm(*cfg)) ? 0 : cfg->n_joints;
+    const size_t np = (size_t)e->n_pad, J = cfg->n_joints, X = cfg->n_obj;
+#define ALLOC(ptr, bytes)                                        \
+    do {                                                         \
+        cudaError_t e_ = cudaMalloc((void **)&(ptr), (bytes));   \
+        if (e_ == cudaSuccess) e_ = cudaMemset((ptr), 0, (bytes)); \
+        if (e_ != cudaSuccess) {                                 \
+            int rc_ = fail(MT_ERR_CUDA, "cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+            mt_destroy(e);                                       \
+            return rc_;                                          \
+        }                                                        \
+    } while (0)
+    ALLOC(e->goals, np * J * 4);
+    ALLOC(e->alive, np * 4);
+    ALLOC(e->total_reward, np * 4);
+    ALLOC(e->counters, np * 4);
+    ALLOC(e->episode, np * 4);
+    ALLOC(e->points, np * X * 3 * 4);
+    ALLOC(e->stats, MT_STATS_WORDS * 8);
+#undef ALLOC
+    fill_params(*cfg, e->base);
+    e->base.goals = e->goals;
+    e->base.alive = e->alive;
+    e->base.total_reward = e->total_reward;
+    e->base.counters = e->counters;
+    e->base.episode = e->episode;
+    e->base.points = e->points;
+    e->base.stats = e->stats;
+    e->base.n = e->n;
+    e->base.tile_begin = 0;
+    e->base.tile_end = e->n_tiles;
+    *out = e;
+    return MT_OK;
+}
+
+extern "C" int mt_destroy(mt_env *e) {
+    if (!e) return MT_OK;
+    DeviceGuard guard(e->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(e->goals); cudaFree(e->alive); cudaFree(e->total_reward); cudaFree(e->counters);
+    cudaFree(e->episode); cudaFree(e->points); cudaFree(e->stats);
+    cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
+    for (auto &s : e->hs) if (s) cudaStreamDestroy(s);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+    return MT_OK;
+}
+
+extern "C" int mt_get_config(const mt_env *e, mt_config *out) {
+    if (!e || !out) return fail(MT_ERR_INVALID, "NULL argument");
+    *out = e->cfg;
+    return MT_OK;
+}
+
+// ----------------------------------------------------------------------------
+// helper kernels (not on the hot path; one thread per env, plain accesses)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pose_of(const StepParams &P, int arm, const float *g, Frames &f, float *jout) {
+    // final pose only: the same code as the step kernel with no interior sub-poses
+    switch (arm) {
+        case 0: ref_arm(g, g, 1, 0.f, f, jout); break;
+#define MT_CASE(JJ) case JJ: { StepParams Q = P; Q.substeps = 1; generic_arm<JJ>(Q, g, g, f, jout); } break;
+        MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8)
+#undef MT_CASE
+    }
+}
+
+__global__ void reset_kernel(const __grid_constant__ StepParams P, const uint8_t *mask) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n) return;
+    if (mask && !mask[env]) return;
+    const int x = P.n_obj, J = P.n_joints;
+    const uint32_t ep = P.episode[env];
+    P.episode[env] = ep + 1u;
+    float *row = P.points + env * 3 * x;
+    for (int pt = 0; pt < x; ++pt) {
+        float px, py, pz;
+        if (P.obj_stream) {
+            const float *src = P.obj_stream + (((long long)(ep % (uint32_t)P.obj_sets) * P.n + env) * x + pt) * 3;
+            px = src[0]; py = src[1]; pz = src[2];
+        } else {
+            sample_point(P, P.env_id_base + env, ep, pt, px, py, pz);
+        }
+        row[pt * 3 + 0] = px; row[pt * 3 + 1] = py; row[pt * 3 + 2] = pz;
+    }
+    for (int i = 0; i < J; ++i) P.goals[env * J + i] = 0.f;           // manytor.py:220
+    P.total_reward[env] = 0.f;                                        // manytor.py:221
+    P.alive[env] = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);        // manytor.py:222
+    P.counters[env] = 0u;
+}
+
+__global__ void observe_kernel(const __grid_constant__ StepParams P, int arm, float *obs) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n) return;
+    const int x = P.n_obj, J = P.n_joints;
+    float g[MT_MAX_JOINTS];
+    for (int i = 0; i < J; ++i) g[i] = P.goals[env * J + i];
+    Frames f;
+    pose_of(P, arm, g, f, nullptr);
+    const uint32_t alive = P.alive[env];
+    const float *row = P.points + env * 3 * x;
+    float *dst = obs + env * 3 * x;
+    for (int pt = 0; pt < x; ++pt) {
+        float px = row[pt * 3], py = row[pt * 3 + 1], pz = row[pt * 3 + 2];
+        one_objective<true>(px, py, pz, f, P.catch_tol, (alive >> pt) & 1u);
+        dst[pt * 3] = px; dst[pt * 3 + 1] = py; dst[pt * 3 + 2] = pz;
+    }
+}
+
+__global__ void joints_kernel(const __grid_constant__ StepParams P, int arm, const float *goals, long long m, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int J = P.n_joints;
+    float g[MT_MAX_JOINTS], jb[MT_MAX_JOINTS * 3];
+    for (int k = 0; k < J; ++k) g[k] = goals[i * J + k];
+    Frames f;
+    pose_of(P, arm, g, f, jb);
+    for (int k = 0; k < J * 3; ++k) out[i * J * 3 + k] = jb[k];
+}
+
+__global__ void set_points_kernel(const __grid_constant__ StepParams P, const float *src, const uint8_t *mask) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = 3LL * P.n_obj;
+    if (i >= P.n * row) return;
+    if (mask && !mask[i / row]) return;
+    P.points[i] = src[i];
+}
+
+__global__ void get_points_kernel(const __grid_constant__ StepParams P, float *dst, int zero_dead) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = 3LL * P.n_obj;
+    if (i >= P.n * row) return;
+    const long long env = i / row;
+    const int pt = (int)((i - env * row) / 3);
+    const bool dead = zero_dead && !((P.alive[env] >> pt) & 1u);      // manytor.py:148
+    dst[i] = dead ? 0.f : P.points[i];
+}
+
+__global__ void set_state_kernel(const __grid_constant__ StepParams P, const float *goals, const uint32_t *alive,
+                                 const float *total, const int32_t *eplen, const uint8_t *mask) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n) return;
+    if (mask && !mask[env]) return;
+    const int J = P.n_joints;
+    if (goals) for (int i = 0; i < J; ++i) P.goals[env * J + i] = goals[env * J + i];
+    if (alive) P.alive[env] = alive[env];
+    if (total) P.total_reward[env] = total[env];
+    if (eplen) P.counters[env] = (P.counters[env] & 0xffff0000u) | (uint32_t)min(max(eplen[env], 0), 65535);
+}
+
+__global__ void get_state_kernel(const __grid_constant__ StepParams P, float *goals, uint32_t *alive, float *total,
+                                 int32_t *eplen) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n) return;
+    const int J = P.n_joints;
+    if (goals) for (int i = 0; i < J; ++i) goals[env * J + i] = P.goals[env * J + i];
+    if (alive) alive[env] = P.alive[env];
+    if (total) total[env] = P.total_reward[env];
+    if (eplen) eplen[env] = (int32_t)(P.counters[env] & 0xffffu);
+}
+
+__global__ void sample_actions_kernel(const __grid_constant__ StepParams P, float *actions) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= P.n) return;
+    float a[MT_MAX_JOINTS];
+    draw_actions(P, P.env_id_base + env, P.n_joints, a);
+    for (int i = 0; i < P.n_joints; ++i) actions[env * P.n_joints + i] = a[i];
+}
+
+// stats: finished-episode counters + a block/warp-shuffle reduction of the
+// in-progress total_reward, written as MT_STATS_WORDS int64.
+__global__ void stats_kernel(const __grid_constant__ StepParams P, long long env_steps, long long *out) {
+    long long local = 0;
+    for (long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x; env < P.n;
+         env += (long long)gridDim.x * blockDim.x)
+        local += (long long)P.total_reward[env];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ long long part[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) part[warp] = local;
+    __syncthreads();
+    if (warp == 0) {
+        local = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+        if (lane == 0) atomicAdd((unsigned long long *)(out + 7), (unsigned long long)local);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 7)
+        out[threadIdx.x] = threadIdx.x == 0 ? env_steps : (long long)P.stats[threadIdx.x];
+}
+
+__global__ void fk_kernel(const __grid_constant__ StepParams P, int mode, const float *goals, long long m, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int J = P.n_joints;
+    float R[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}}, t[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < mode && k < J; ++k) {
+        float sk, ck;
+        sincos_deg(goals[i * J + k], sk, ck);
+        const JointConst q = P.arm[k];
+        float c = fmaf(ck, q.co, -(sk * q.so)), s = fmaf(sk, q.co, ck * q.so);
+        for (int r = 0; r < 3; ++r) {
+            float u = fmaf(R[r][0], c, R[r][1] * s), v = fmaf(R[r][1], c, -(R[r][0] * s)), r2 = R[r][2];
+            t[r] = fmaf(q.a, u, fmaf(q.d, r2, t[r]));
+            R[r][0] = u;
+            R[r][1] = fmaf(v, q.ca, r2 * q.sa);
+            R[r][2] = fmaf(r2, q.ca, -(v * q.sa));
+        }
+    }
+    float *o = out + i * 16;
+    for (int r = 0; r < 3; ++r) {
+        o[r * 4 + 0] = R[r][0]; o[r * 4 + 1] = R[r][1]; o[r * 4 + 2] = R[r][2]; o[r * 4 + 3] = t[r];
+    }
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+
+__global__ void dh_kernel(const float *params, long long m, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float a = params[i * 4], alfa = params[i * 4 + 1], d = params[i * 4 + 2], th = params[i * 4 + 3];
+    float st, ct, sa, ca;
+    sincosf(th, &st, &ct);
+    sincosf(alfa, &sa, &ca);
+    float *o = out + i * 16;
+    o[0] = ct; o[1] = -st * ca; o[2] = st * sa; o[3] = a * ct;
+    o[4] = st; o[5] = ct * ca; o[6] = -ct * sa; o[7] = a * st;
+    o[8] = 0.f; o[9] = sa; o[10] = ca; o[11] = d;
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+
+__global__ void r_theta_kernel(const float *v1, const float *v2, long long m, float *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float dx = fabsf(v1[i * 3] - v2[i * 3]), dy = fabsf(v1[i * 3 + 1] - v2[i * 3 + 1]),
+          dz = fabsf(v1[i * 3 + 2] - v2[i * 3 + 2]);
+    out[i * 2] = atan2_deg_pos(dx, dy);
+    out[i * 2 + 1] = atan2_deg_pos(fast_sqrt(fmaf(dx, dx, dy * dy)), dz);
+}
+
+// ----------------------------------------------------------------------------
+// step dispatch
+// ----------------------------------------------------------------------------
+typedef void (*StepFn)(const StepParams);
+
+template <int ARM, int X>
+static StepFn pick_flags(bool rnd, bool wobs) {
+    if (rnd) return wobs ? step_kernel<ARM, X, true, true> : step_kernel<ARM, X, true, false>;
+    return wobs ? step_kernel<ARM, X, false, true> : step_kernel<ARM, X, false, false>;
+}
+
+template <int ARM>
+static StepFn pick_x(int x, bool rnd, bool wobs) {
+    switch (x) {
+        case 10: return pick_flags<ARM, 10>(rnd, wobs);
+        case 20: return pick_flags<ARM, 20>(rnd, wobs);
+        default: return pick_flags<ARM, 0>(rnd, wobs);
+    }
+}
+
+static StepFn pick_kernel(int arm, int x, bool rnd, bool wobs) {
+    switch (arm) {
+        case 0: return pick_x<0>(x, rnd, wobs);
+        case 2: return pick_flags<2, 0>(rnd, wobs);
+        case 3: return pick_flags<3, 0>(rnd, wobs);
+        case 4: return pick_flags<4, 0>(rnd, wobs);
+        case 5: return pick_flags<5, 0>(rnd, wobs);
+        case 6: return pick_x<6>(x, rnd, wobs);
+        case 7: return pick_flags<7, 0>(rnd, wobs);
+        case 8: return pick_flags<8, 0>(rnd, wobs);
+    }
+    return nullptr;
+}
+
+static int check_ptr(const void *p, const char *name, bool required) {
+    if (!p) return required ? fail(MT_ERR_INVALID, "%s is NULL", name) : MT_OK;
+    if (((uintptr_t)p & 15u) != 0) return fail(MT_ERR_INVALID, "%s must be 16-byte aligned", name);
+    return MT_OK;
+}
+
+// launch the fused step kernel over tiles [t0, t1)
+static int launch_step(mt_env *e, const float *actions, float *obs, float *reward, uint8_t *done, float *joints,
+                       bool rnd, long long t0, long long t1, cudaStream_t st) {
+    StepParams P = e->base;
+    P.actions = actions;
+    P.obs = obs;
+    P.reward = reward;
+    P.done = done;
+    P.joints = joints;
+    P.obj_stream = e->obj_stream;
+    P.obj_sets = e->obj_sets;
+    P.step_lo = (uint32_t)e->step_index;
+    P.step_hi = (uint32_t)(e->step_index >> 32);
+    P.tile_begin = t0;
+    P.tile_end = t1;
+    StepFn fn = pick_kernel(e->arm, e->cfg.n_obj, rnd, obs != nullptr);
+    if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
+    const size_t smem = (size_t)kWarpsPerBlock * P.tile_bytes + kWarpsPerBlock * sizeof(uint64_t);
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long tiles = t1 - t0;
+    const unsigned grid = (unsigned)((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    fn<<<grid, kWarpsPerBlock * kTile, smem, st>>>(P);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+static inline unsigned blocks_for(long long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+extern "C" int mt_reset(mt_env *e, const uint8_t *mask_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    StepParams P = e->base;
+    P.obj_stream = e->obj_stream;
+    P.obj_sets = e->obj_sets;
+    reset_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(P, mask_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    e->was_reset = true;
+    return MT_OK;
+}
+
+extern "C" int mt_observe(mt_env *e, float *obs_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (int rc = check_ptr(obs_dev, "obs_dev", true)) return rc;
+    if (!e->was_reset) return fail(MT_ERR_STATE, "mt_observe before mt_reset (the reference raises IndexError here, manytor.py:143)");
+    DeviceGuard guard(e->cfg.device);
+    observe_kernel<<<blocks_for(e->n, 128), 128, 0, (cudaStream_t)stream>>>(e->base, e->arm, obs_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+static int timing_begin(mt_env *e, cudaStream_t st) {
+    if (!e->timing) return MT_OK;
+    if (!e->ev0) { CU(cudaEventCreate(&e->ev0)); CU(cudaEventCreate(&e->ev1)); }
+    CU(cudaEventRecord(e->ev0, st));
+    return MT_OK;
+}
+static int timing_end(mt_env *e, cudaStream_t st) {
+    if (!e->timing) return MT_OK;
+    CU(cudaEventRecord(e->ev1, st));
+    e->ev_valid = true;
+    return MT_OK;
+}
+
+extern "C" int mt_step(mt_env *e, const float *actions_dev, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+                       float *joints_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (!e->was_reset) return fail(MT_ERR_STATE, "mt_step before mt_reset (the reference raises IndexError here, manytor.py:143)");
+    int rc;
+    if ((rc = check_ptr(actions_dev, "actions_dev", true))) return rc;
+    if ((rc = check_ptr(obs_dev, "obs_dev", false))) return rc;
+    if (!reward_dev || !done_dev) return fail(MT_ERR_INVALID, "reward_dev/done_dev is NULL");
+    DeviceGuard guard(e->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = timing_begin(e, st))) return rc;
+    if ((rc = launch_step(e, actions_dev, obs_dev, reward_dev, done_dev, joints_dev, false, 0, e->n_tiles, st))) return rc;
+    if ((rc = timing_end(e, st))) return rc;
+    e->step_index++;
+    e->env_steps += e->n;
+    return MT_OK;
+}
+
+extern "C" int mt_sample_actions(mt_env *e, float *actions_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (int rc = check_ptr(actions_dev, "actions_dev", true)) return rc;
+    DeviceGuard guard(e->cfg.device);
+    StepParams P = e->base;
+    P.step_lo = (uint32_t)e->step_index;
+    P.step_hi = (uint32_t)(e->step_index >> 32);
+    sample_actions_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(P, actions_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_rollout_random(mt_env *e, int32_t n_steps, float *obs_dev, float *reward_dev, uint8_t *done_dev,
+                                 void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (!e->was_reset) return fail(MT_ERR_STATE, "mt_rollout_random before mt_reset");
+    if (n_steps < 0) return fail(MT_ERR_INVALID, "n_steps < 0");
+    int rc;
+    if ((rc = check_ptr(obs_dev, "obs_dev", false))) return rc;
+    if (!reward_dev || !done_dev) return fail(MT_ERR_INVALID, "reward_dev/done_dev is NULL");
+    DeviceGuard guard(e->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = timing_begin(e, st))) return rc;
+    for (int s = 0; s < n_steps; ++s) {
+        if ((rc = launch_step(e, nullptr, obs_dev, reward_dev, done_dev, nullptr, true, 0, e->n_tiles, st))) return rc;
+        e->step_index++;
+        e->env_steps += e->n;
+    }
+    return timing_end(e, st);
+}
+
+extern "C" int mt_host_alloc(void **out, uint64_t bytes) {
+    if (!out) return fail(MT_ERR_INVALID, "out is NULL");
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MT_OK;
+}
+extern "C" int mt_host_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return MT_OK;
+}
+
+extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_host, float *reward_host,
+                            uint8_t *done_host) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (!e->was_reset) return fail(MT_ERR_STATE, "mt_step_host before mt_reset");
+    if (!actions_host || !reward_host || !done_host) return fail(MT_ERR_INVALID, "NULL host buffer");
+    DeviceGuard guard(e->cfg.device);
+    const size_t J = e->cfg.n_joints, R = 3 * (size_t)e->cfg.n_obj;
+    if (!e->h_actions) {
+        CU(cudaMalloc((void **)&e->h_actions, (size_t)e->n_pad * J * 4));
+        CU(cudaMalloc((void **)&e->h_obs, (size_t)e->n_pad * R * 4));
+        CU(cudaMalloc((void **)&e->h_reward, (size_t)e->n_pad * 4));
+        CU(cudaMalloc((void **)&e->h_done, (size_t)e->n_pad));
+        for (auto &s : e->hs) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
+    CU(cudaDeviceSynchronize());
+    // chunks of whole tiles, round-robin over the streams: H2D(actions) -> step -> D2H(results)
+    const long long chunks = e->n_tiles < 16 ? 1 : 16;
+    const long long per = (e->n_tiles + chunks - 1) / chunks;
+    int k = 0;
+    for (long long t0 = 0; t0 < e->n_tiles; t0 += per, ++k) {
+        const long long t1 = (t0 + per < e->n_tiles) ? t0 + per : e->n_tiles;
+        const long long e0 = t0 * kTile, e1 = (t1 * kTile < e->n) ? t1 * kTile : e->n, cnt = e1 - e0;
+        cudaStream_t st = e->hs[k % mt_env::kStreams];
+        CU(cudaMemcpyAsync(e->h_actions + e0 * J, actions_host + e0 * J, cnt * J * 4, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, e->h_reward, e->h_done, nullptr, false,
+                                 t0, t1, st))
+            return rc;
+        if (obs_host) CU(cudaMemcpyAsync(obs_host + e0 * R, e->h_obs + e0 * R, cnt * R * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(reward_host + e0, e->h_reward + e0, cnt * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(done_host + e0, e->h_done + e0, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (auto &s : e->hs) CU(cudaStreamSynchronize(s));
+    e->step_index++;
+    e->env_steps += e->n;
+    return MT_OK;
+}
+
+extern "C" int mt_set_points(mt_env *e, const float *points_dev, const uint8_t *mask_dev, void *stream) {
+    if (!e || !points_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(e->cfg.device);
+    set_points_kernel<<<blocks_for(e->n * 3 * e->cfg.n_obj), 256, 0, (cudaStream_t)stream>>>(e->base, points_dev, mask_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_get_points(mt_env *e, float *points_dev, int32_t zero_dead, void *stream) {
+    if (!e || !points_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(e->cfg.device);
+    get_points_kernel<<<blocks_for(e->n * 3 * e->cfg.n_obj), 256, 0, (cudaStream_t)stream>>>(e->base, points_dev, zero_dead);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_set_state(mt_env *e, const float *goals_dev, const uint32_t *alive_dev, const float *total_reward_dev,
+                            const int32_t *ep_len_dev, const uint8_t *mask_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    set_state_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(e->base, goals_dev, alive_dev, total_reward_dev,
+                                                                          ep_len_dev, mask_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_get_state(mt_env *e, float *goals_dev, uint32_t *alive_dev, float *total_reward_dev,
+                            int32_t *ep_len_dev, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    get_state_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(e->base, goals_dev, alive_dev, total_reward_dev,
+                                                                          ep_len_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_set_objective_stream(mt_env *e, const float *points_dev, int32_t n_sets) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (points_dev && n_sets < 1) return fail(MT_ERR_INVALID, "n_sets must be >= 1");
+    e->obj_stream = points_dev;
+    e->obj_sets = points_dev ? n_sets : 0;
+    return MT_OK;
+}
+
+extern "C" int mt_fetch_env(mt_env *e, int64_t index, float *goals_host, float *joints_host, float *points_host,
+                            uint32_t *alive_host, float *total_reward_host) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    if (index < 0 || index >= e->n) return fail(MT_ERR_INVALID, "env index %lld outside [0, %lld)", (long long)index, e->n);
+    DeviceGuard guard(e->cfg.device);
+    const size_t J = e->cfg.n_joints, X = e->cfg.n_obj;
+    CU(cudaDeviceSynchronize());
+    uint32_t alive = 0;
+    CU(cudaMemcpy(&alive, e->alive + index, 4, cudaMemcpyDeviceToHost));
+    if (alive_host) *alive_host = alive;
+    if (goals_host) CU(cudaMemcpy(goals_host, e->goals + index * J, J * 4, cudaMemcpyDeviceToHost));
+    if (total_reward_host) CU(cudaMemcpy(total_reward_host, e->total_reward + index, 4, cudaMemcpyDeviceToHost));
+    if (points_host) {
+        CU(cudaMemcpy(points_host, e->points + index * X * 3, X * 12, cudaMemcpyDeviceToHost));
+        for (size_t p = 0; p < X; ++p)
+            if (!((alive >> p) & 1u)) points_host[p * 3] = points_host[p * 3 + 1] = points_host[p * 3 + 2] = 0.f;  // manytor.py:148
+    }
+    if (joints_host) {
+        float *tmp = nullptr;
+        CU(cudaMalloc((void **)&tmp, J * 12));
+        joints_kernel<<<1, 32>>>(e->base, e->arm, e->goals + index * J, 1, tmp);
+        cudaError_t ce = cudaMemcpy(joints_host, tmp, J * 12, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        CU(ce);
+        e->launches++;
+    }
+    return MT_OK;
+}
+
+extern "C" int mt_stats_device(mt_env *e, int64_t *stats_dev, void *stream) {
+    if (!e || !stats_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(e->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(stats_dev, 0, MT_STATS_WORDS * 8, st));
+    stats_kernel<<<148, 256, 0, st>>>(e->base, e->env_steps, (long long *)stats_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_stats_host(mt_env *e, mt_stats *out) {
+    if (!e || !out) return fail(MT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(e->cfg.device);
+    int64_t *tmp = nullptr;
+    CU(cudaMalloc((void **)&tmp, MT_STATS_WORDS * 8));
+    CU(cudaDeviceSynchronize());
+    int rc = mt_stats_device(e, tmp, nullptr);
+    cudaError_t ce = cudaSuccess;
+    if (rc == MT_OK) ce = cudaMemcpy(out, tmp, MT_STATS_WORDS * 8, cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (rc) return rc;
+    CU(ce);
+    return MT_OK;
+}
+
+extern "C" int mt_stats_clear(mt_env *e, void *stream) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    CU(cudaMemsetAsync(e->stats, 0, MT_STATS_WORDS * 8, (cudaStream_t)stream));
+    e->env_steps = 0;
+    return MT_OK;
+}
+
+extern "C" int mt_fk(const mt_config *cfg, int32_t mode, const float *goals_dev, float *out_dev, int64_t m, void *stream) {
+    if (!cfg || !goals_dev || !out_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    mt_config c = *cfg;
+    if (c.n_envs < 1) c.n_envs = 1;
+    if (int rc = validate(c)) return rc;
+    if (mode < 1 || mode > c.n_joints) return fail(MT_ERR_INVALID, "mode must be in [1, %d]", c.n_joints);
+    if (m <= 0) return MT_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MT_ERR_NO_DEVICE, "no CUDA device; manytor_b200 has no CPU fallback");
+    DeviceGuard guard(c.device);
+    StepParams P;
+    fill_params(c, P);
+    fk_kernel<<<blocks_for(m), 256, 0, (cudaStream_t)stream>>>(P, mode, goals_dev, m, out_dev);
+    CU(cudaGetLastError());
+    return MT_OK;
+}
+
+extern "C" int mt_dh(const float *params_dev, float *out_dev, int64_t m, void *stream) {
+    if (!params_dev || !out_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    if (m <= 0) return MT_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MT_ERR_NO_DEVICE, "no CUDA device; manytor_b200 has no CPU fallback");
+    dh_kernel<<<blocks_for(m), 256, 0, (cudaStream_t)stream>>>(params_dev, m, out_dev);
+    CU(cudaGetLastError());
+    return MT_OK;
+}
+
+extern "C" int mt_joints(mt_env *e, const float *goals_dev, float *out_dev, int64_t m, void *stream) {
+    if (!e || !goals_dev || !out_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    if (m <= 0) return MT_OK;
+    DeviceGuard guard(e->cfg.device);
+    joints_kernel<<<blocks_for(m, 128), 128, 0, (cudaStream_t)stream>>>(e->base, e->arm, goals_dev, m, out_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    return MT_OK;
+}
+
+extern "C" int mt_r_theta(const float *v1_dev, const float *v2_dev, float *out_dev, int64_t m, void *stream) {
+    if (!v1_dev || !v2_dev || !out_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    if (m <= 0) return MT_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(MT_ERR_NO_DEVICE, "no CUDA device; manytor_b200 has no CPU fallback");
+    r_theta_kernel<<<blocks_for(m), 256, 0, (cudaStream_t)stream>>>(v1_dev, v2_dev, m, out_dev);
+    CU(cudaGetLastError());
+    return MT_OK;
+}
+
+extern "C" int64_t mt_launch_count(const mt_env *e) { return e ? e->launches : 0; }
+
+// B = 12J + 24X + 21 with actions read from HBM and obs
+// written; minus 4J when actions are drawn in-kernel, minus 12X without obs.
+extern "C" int64_t mt_bytes_per_env_step(const mt_env *e, int32_t actions_from_hbm, int32_t obs_written) {
+    if (!e) return 0;
+    const int64_t J = e->cfg.n_joints, X = e->cfg.n_obj;
+    int64_t b = 8 * J + 12 * X + 21;  // goals r+w, points r, alive r+w, reward w, done w, total_reward r+w
+    if (actions_from_hbm) b += 4 * J;
+    if (obs_written) b += 12 * X;
+    return b;
+}
+
+extern "C" int mt_set_timing(mt_env *e, int32_t enabled) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    e->timing = enabled != 0;
+    e->ev_valid = false;
+    return MT_OK;
+}
+
+extern "C" int mt_last_kernel_ms(mt_env *e, float *ms_out) {
+    if (!e || !ms_out) return fail(MT_ERR_INVALID, "NULL argument");
+    if (!e->ev_valid) return fail(MT_ERR_STATE, "no timed launch recorded (mt_set_timing)");
+    DeviceGuard guard(e->cfg.device);
+    CU(cudaEventSynchronize(e->ev1));
+    CU(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
+    return MT_OK;
+}

@@ -1,0 +1,478 @@
+// The fused step kernel: one launch = Environment.step for every env of a shard.
+//
+// Restates, per environment (lane), the reference's
+//   step          manytor.py:255-260
+//   action        manytor.py:175-213   (25 interpolated poses, ground flag, reward)
+//   fk / dh       manytor.py:35-53, 25-32 (closed form for the reference arm,
+//                                          z-row / affine chain for a generic DH table)
+//   get_observations / r_theta  manytor.py:141-153, 17-22
+//   is_done       manytor.py:155-173
+//   reset         manytor.py:219-241   (auto-reset with on-device objective refresh)
+//
+// Mapping: one warp owns a tile of 32 consecutive envs, one lane per env.  The
+// tile's objectives ([32][X][3] fp32, 120 B per env at X=10) are fetched from HBM
+// by ONE TMA bulk copy into shared memory while the lanes do the kinematics
+// (which need no objectives); observations are written in place over the
+// objectives and leave by ONE TMA bulk store, so the row-major [N][3X] layouts
+// are moved with full-line transactions and no per-lane strided access.  All
+// other state is fp32/u32 structure-of-arrays read and written once per step
+// with coalesced (vector) accesses.
+#pragma once
+#include "../../include/manytor_b200.h"
+#include "mt_math.cuh"
+#include "mt_ptx.cuh"
+
+namespace mt {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kTile = 32;
+
+enum StepFlags : int32_t {
+    kTerminateOnGround = 1,
+    kAutoReset = 2,
+    kObsAfterReset = 4,
+};
+
+struct JointConst {
+    float a, d, ca, sa;  // DH row: link length, offset, cos/sin(alpha)
+    float co, so;        // cos/sin(theta offset)
+};
+
+struct StepParams {
+    // state (HBM, padded to a whole number of tiles)
+    float *goals;            // [Npad][J]
+    uint32_t *alive;         // [Npad]
+    float *total_reward;     // [Npad]
+    uint32_t *counters;      // [Npad]  ep_len (low 16, saturating) | ground steps (high 16, saturating)
+    uint32_t *episode;       // [Npad]  resets so far (touched only on reset)
+    float *points;           // [Npad][X][3]
+    // per-step I/O
+    const float *actions;    // [N][J] or nullptr when drawn in-kernel
+    float *obs;              // [N][3X]
+    float *reward;           // [N]
+    uint8_t *done;           // [N]
+    float *joints;           // [N][J][3] or nullptr
+    const float *obj_stream; // [sets][N][X][3] or nullptr
+    unsigned long long *stats;
+    long long n;
+    long long tile_begin, tile_end;
+    long long env_id_base;
+    uint32_t seed_lo, seed_hi;
+    uint32_t step_lo, step_hi;
+    int32_t n_obj, n_joints, substeps, horizon, flags, obj_sets;
+    int32_t action_low;
+    uint32_t action_span;
+    float radius, catch_tol, inv_div;
+    int32_t obs_frame, ground_a, ground_b, catch_frame;
+    float zero_anchor[3];
+    JointConst arm[MT_MAX_JOINTS];
+    uint32_t tile_bytes;
+};
+
+// ---------------------------------------------------------------------------
+// kinematics
+// ---------------------------------------------------------------------------
+struct Frames {
+    float anchor[3];   // obs frame origin   (reference: elbow, manytor.py:143)
+    float catcher[3];  // catch frame origin (reference: terminal, manytor.py:162)
+    float zmin;        // min z of the two ground frames over all sub-poses (manytor.py:191)
+};
+
+// rotate (c, s) by minus delta: angle <- angle - d
+__device__ __forceinline__ void rot_back(float &c, float &s, float cd, float sd) {
+    float nc = fmaf(c, cd, s * sd);
+    s = fmaf(s, cd, -(c * sd));
+    c = nc;
+}
+
+// Reference arm, closed form: with alpha = -+pi/2 the chain of
+// manytor.py:42-52 collapses to
+//   frame2 = (0, 0, 4.3)
+//   elbow  = (24.3 c0 s1, 24.3 s0 s1, 4.3 + 24.3 c1)
+//   ee     = elbow + 27 (s3 (c0 c1 c2 - s0 s2) + c3 c0 s1,
+//                        s3 (s0 c1 c2 + c0 s2) + c3 s0 s1,
+//                        c3 c1 - s3 s1 c2)
+// (theta3 before its -pi/2 offset).  Only the z components are needed at the 24
+// interior sub-poses; they depend on theta1..3 only and the route is linear in
+// angle, so their sin/cos follow by one plane rotation per joint per sub-pose,
+// run backwards from the exact final pose.
+__device__ __forceinline__ void ref_arm(const float *g, const float *a, int substeps, float inv_div, Frames &f,
+                                        float *jout /* 12 floats or nullptr */) {
+    float s0, c0, s1, c1, s2, c2, s3, c3;
+    sincos_deg(a[0], s0, c0);
+    sincos_deg(a[1], s1, c1);
+    sincos_deg(a[2], s2, c2);
+    sincos_deg(a[3], s3, c3);
+    const float L1 = 24.3f, L2 = 27.0f, H = 4.3f;
+    float ez = fmaf(L1, c1, H);
+    float k = L1 * s1;
+    float ex = k * c0, ey = k * s0;
+    float c1c2 = c1 * c2;
+    float ux = fmaf(c0, c1c2, -(s0 * s2));
+    float uy = fmaf(s0, c1c2, c0 * s2);
+    float s1c3 = s1 * c3;
+    float tx = fmaf(L2, fmaf(s3, ux, c0 * s1c3), ex);
+    float ty = fmaf(L2, fmaf(s3, uy, s0 * s1c3), ey);
+    float tz = fmaf(L2, fmaf(c3, c1, -((s3 * s1) * c2)), ez);
+    f.anchor[0] = ex; f.anchor[1] = ey; f.anchor[2] = ez;
+    f.catcher[0] = tx; f.catcher[1] = ty; f.catcher[2] = tz;
+    if (jout) {
+        jout[0] = 0.f; jout[1] = 0.f; jout[2] = 0.f;
+        jout[3] = 0.f; jout[4] = 0.f; jout[5] = H;
+        jout[6] = ex; jout[7] = ey; jout[8] = ez;
+        jout[9] = tx; jout[10] = ty; jout[11] = tz;
+    }
+    float zmin = fminf(ez, tz);
+    float sd1, cd1, sd2, cd2, sd3, cd3;
+    sincos_deg((a[1] - g[1]) * inv_div, sd1, cd1);
+    sincos_deg((a[2] - g[2]) * inv_div, sd2, cd2);
+    sincos_deg((a[3] - g[3]) * inv_div, sd3, cd3);
+#pragma unroll 4
+    for (int p = 1; p < substeps; ++p) {
+        rot_back(c1, s1, cd1, sd1);
+        rot_back(c2, s2, cd2, sd2);
+        rot_back(c3, s3, cd3, sd3);
+        float ze = fmaf(L1, c1, H);
+        float zt = fmaf(L2, fmaf(c3, c1, -((s3 * s1) * c2)), ze);
+        zmin = fminf(zmin, fminf(ze, zt));
+    }
+    f.zmin = zmin;
+}
+
+// Generic J-joint DH chain (the reference's "pluggable fk", README.md:20).
+// Final pose: 3x4 affine prefix products, origins of every frame.  Sub-poses:
+// only the z row e_z^T A_1 ... A_k is propagated (10 FMA-class ops per joint);
+// it does not depend on the first joint's angle.
+template <int J>
+__device__ __forceinline__ void generic_arm(const StepParams &P, const float *g, const float *a, Frames &f,
+                                            float *jout /* J*3 floats or nullptr */) {
+    float c[J], s[J];
+#pragma unroll
+    for (int i = 0; i < J; ++i) {
+        float si, ci;
+        sincos_deg(a[i], si, ci);
+        c[i] = fmaf(ci, P.arm[i].co, -(si * P.arm[i].so));
+        s[i] = fmaf(si, P.arm[i].co, ci * P.arm[i].so);
+    }
+    // rows of the accumulated transform: R (3x3) and t (3)
+    float R[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    float t[3] = {0.f, 0.f, 0.f};
+    float zA = 0.f, zB = 0.f;
+    if (jout) { jout[0] = 0.f; jout[1] = 0.f; jout[2] = 0.f; }
+    if (P.obs_frame == 0) { f.anchor[0] = f.anchor[1] = f.anchor[2] = 0.f; }
+    if (P.catch_frame == 0) { f.catcher[0] = f.catcher[1] = f.catcher[2] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < J; ++i) {
+        const JointConst q = P.arm[i];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float u = fmaf(R[r][0], c[i], R[r][1] * s[i]);
+            float v = fmaf(R[r][1], c[i], -(R[r][0] * s[i]));
+            float r2 = R[r][2];
+            t[r] = fmaf(q.a, u, fmaf(q.d, r2, t[r]));
+            R[r][0] = u;
+            R[r][1] = fmaf(v, q.ca, r2 * q.sa);
+            R[r][2] = fmaf(r2, q.ca, -(v * q.sa));
+        }
+        const int frame = i + 1;
+        if (frame == P.obs_frame) { f.anchor[0] = t[0]; f.anchor[1] = t[1]; f.anchor[2] = t[2]; }
+        if (frame == P.catch_frame) { f.catcher[0] = t[0]; f.catcher[1] = t[1]; f.catcher[2] = t[2]; }
+        if (frame == P.ground_a) zA = t[2];
+        if (frame == P.ground_b) zB = t[2];
+        if (jout && frame >= 2) { jout[(frame - 1) * 3 + 0] = t[0]; jout[(frame - 1) * 3 + 1] = t[1]; jout[(frame - 1) * 3 + 2] = t[2]; }
+    }
+    float zmin = fminf(zA, zB);
+    float cd[J], sd[J];
+#pragma unroll
+    for (int i = 1; i < J; ++i) sincos_deg((a[i] - g[i]) * P.inv_div, sd[i], cd[i]);
+    for (int p = 1; p < P.substeps; ++p) {
+        float r0 = 0.f, r1 = P.arm[0].sa, r2 = P.arm[0].ca, tz = P.arm[0].d;
+        float za = (P.ground_a <= 1) ? ((P.ground_a == 1) ? tz : 0.f) : 0.f;
+        float zb = (P.ground_b <= 1) ? ((P.ground_b == 1) ? tz : 0.f) : 0.f;
+#pragma unroll
+        for (int i = 1; i < J; ++i) {
+            rot_back(c[i], s[i], cd[i], sd[i]);
+            const JointConst q = P.arm[i];
+            float u = fmaf(r0, c[i], r1 * s[i]);
+            float v = fmaf(r1, c[i], -(r0 * s[i]));
+            tz = fmaf(q.a, u, fmaf(q.d, r2, tz));
+            r0 = u;
+            r1 = fmaf(v, q.ca, r2 * q.sa);
+            r2 = fmaf(r2, q.ca, -(v * q.sa));
+            if (i + 1 == P.ground_a) za = tz;
+            if (i + 1 == P.ground_b) zb = tz;
+        }
+        zmin = fminf(zmin, fminf(za, zb));
+    }
+    f.zmin = zmin;
+}
+
+// ---------------------------------------------------------------------------
+// observations + catch for one objective (manytor.py:141-153, 17-22, 158-168)
+// ---------------------------------------------------------------------------
+template <bool WOBS>
+__device__ __forceinline__ bool one_objective(float &px, float &py, float &pz, const Frames &f, float tol,
+                                              bool alive) {
+    // catch: inclusive axis-aligned cube around the catch frame (math.isclose abs_tol)
+    bool caught = (fabsf(f.catcher[0] - px) <= tol) & (fabsf(f.catcher[1] - py) <= tol) &
+                  (fabsf(f.catcher[2] - pz) <= tol);
+    if (WOBS) {
+        float dx = fabsf(f.anchor[0] - px), dy = fabsf(f.anchor[1] - py), dz = fabsf(f.anchor[2] - pz);
+        float h2 = fmaf(dx, dx, dy * dy);
+        float dist = fast_sqrt(fmaf(dz, dz, h2));
+        float h = fast_sqrt(h2);
+        float r = atan2_deg_pos(dx, dy);
+        float th = atan2_deg_pos(h, dz);
+        px = alive ? dist : 0.0f;
+        py = alive ? r : 0.0f;
+        pz = alive ? th : 0.0f;
+    }
+    return caught;
+}
+
+// Vector width for the in-place row walk: the widest power of two (<= 4 floats)
+// dividing the row length 3X, which makes the per-lane row stride odd in
+// vector units and the shared-memory accesses bank-conflict free.
+template <int X> struct RowVec { static constexpr int value = (X % 4 == 0) ? 4 : ((X % 2 == 0) ? 2 : 1); };
+template <> struct RowVec<0> { static constexpr int value = 1; };
+
+template <int V> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int V>
+__device__ __forceinline__ void vload(const float *p, float *v) {
+    using T = typename VecT<V>::type;
+    T t = *reinterpret_cast<const T *>(p);
+    const float *q = reinterpret_cast<const float *>(&t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) v[i] = q[i];
+}
+template <int V>
+__device__ __forceinline__ void vstore(float *p, const float *v) {
+    using T = typename VecT<V>::type;
+    T t;
+    float *q = reinterpret_cast<float *>(&t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) q[i] = v[i];
+    *reinterpret_cast<T *>(p) = t;
+}
+
+// Walk one env's row of objectives in shared memory: V objectives (3 vectors
+// of V floats) per iteration, observations written back in place.  Returns
+// the bitmask of objectives inside the catch cube.
+template <int X, bool WOBS>
+__device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f, float tol, uint32_t alive) {
+    constexpr int V = RowVec<X>::value;
+    uint32_t caught = 0;
+    const int iters = (X ? X : x) / V;
+#pragma unroll
+    for (int it = 0; it < iters; ++it) {
+        float v[3 * V];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) vload<V>(row + (it * 3 + i) * V, v + i * V);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int pt = it * V + j;
+            bool c = one_objective<WOBS>(v[3 * j], v[3 * j + 1], v[3 * j + 2], f, tol, (alive >> pt) & 1u);
+            caught |= c ? (1u << pt) : 0u;
+        }
+        if (WOBS) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) vstore<V>(row + (it * 3 + i) * V, v + i * V);
+        }
+    }
+    return caught;
+}
+
+// ---------------------------------------------------------------------------
+// objective refresh (manytor.py:228-241): uniform in the upper half ball.
+// The reference rejects from the cube; the direct map below has the same
+// distribution: r = R u^(1/3), z/r uniform on [0,1], azimuth uniform.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void sample_point(const StepParams &P, long long gid, uint32_t episode, int pt, float &x,
+                                             float &y, float &z) {
+    Philox u = philox4x32_10((uint32_t)gid, (uint32_t)((unsigned long long)gid >> 32), episode * 32u + (uint32_t)pt,
+                             STREAM_POINTS, P.seed_lo, P.seed_hi);
+    float r = fminf(P.radius * cbrtf(1.0f - uniform01(u.x)), P.radius);
+    float ct = uniform01(u.y);
+    float st = sqrtf(fmaxf(1.0f - ct * ct, 0.0f));
+    float sphi, cphi;
+    sincospif(2.0f * uniform01(u.z), &sphi, &cphi);
+    x = r * st * cphi;
+    y = r * st * sphi;
+    z = r * ct;
+}
+
+__device__ __forceinline__ void draw_actions(const StepParams &P, long long gid, int J, float *a) {
+    const uint32_t lo = (uint32_t)gid, hi = (uint32_t)((unsigned long long)gid >> 32);
+    Philox u = philox4x32_10(lo, hi, P.step_lo, STREAM_ACTIONS ^ P.step_hi, P.seed_lo, P.seed_hi);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i < J) a[i] = (float)uniform_int(w[i], P.action_low, P.action_span);
+    if (J > 4) {
+        Philox u2 = philox4x32_10(lo, hi, P.step_lo, (STREAM_ACTIONS + 1u) ^ P.step_hi, P.seed_lo, P.seed_hi);
+        const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int i = 4; i < MT_MAX_JOINTS; ++i)
+            if (i < J) a[i] = (float)uniform_int(w2[i - 4], P.action_low, P.action_span);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+//   ARM  0 = reference arm closed form (J = 4); else J of the generic chain
+//   X    objectives per env, 0 = run-time P.n_obj
+//   RAND draw actions in-kernel (mt_rollout_random)   WOBS write observations
+// ---------------------------------------------------------------------------
+template <int ARM, int X, bool RAND, bool WOBS>
+__global__ void __launch_bounds__(kWarpsPerBlock *kTile)
+step_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int J = ARM ? ARM : 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long tile = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
+    if (tile >= P.tile_end) return;
+    const long long env0 = tile * kTile, env = env0 + lane;
+    const int x = X ? X : P.n_obj;
+    const int rowlen = 3 * x;
+    float *tile_s = reinterpret_cast<float *>(smem + (size_t)warp * P.tile_bytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)kWarpsPerBlock * P.tile_bytes) + warp;
+    const bool full = env0 + kTile <= P.n;  // warp-uniform
+    const bool valid = env < P.n;
+    const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
+
+    // 1. start the objectives tile on its way: HBM -> shared by one TMA bulk copy
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_load(tile_s, P.points + env0 * rowlen, tile_bytes, bar);
+    }
+    __syncwarp();
+
+    // 2. per-env state and action: coalesced (vector) loads
+    float g[J], a[J];
+    if (J == 4) {
+        float4 t = *reinterpret_cast<const float4 *>(P.goals + env * 4);
+        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < J; ++i) g[i] = P.goals[env * J + i];
+    }
+    if (RAND) {
+        draw_actions(P, P.env_id_base + env, J, a);
+    } else if (!valid) {
+#pragma unroll
+        for (int i = 0; i < J; ++i) a[i] = 0.f;
+    } else if (J == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(P.actions + env * 4));
+        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < J; ++i) a[i] = __ldg(P.actions + env * J + i);
+    }
+    const uint32_t alive0 = P.alive[env];
+    float total = P.total_reward[env];
+    uint32_t cnt = P.counters[env];
+
+    // 3. kinematics while the tile is in flight
+    Frames f;
+    float jbuf[J * 3];
+    float *jout = P.joints ? jbuf : nullptr;
+    if (ARM == 0) ref_arm(g, a, P.substeps, P.inv_div, f, jout);
+    else generic_arm<J>(P, g, a, f, jout);
+    const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
+
+    // 4. objectives: obs2 in place + catch mask
+    mbar_wait(bar, 0);
+    float *row = tile_s + lane * rowlen;
+    const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
+    uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
+
+    // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
+    float rew = (alive1 != alive0) ? 1.0f : 0.0f;
+    rew = neg ? -1.0f : rew;
+    total += rew;
+    uint32_t eplen = min((cnt & 0xffffu) + 1u, 0xffffu);
+    uint32_t gsteps = min((cnt >> 16) + (neg ? 1u : 0u), 0xffffu);
+    bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
+    bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
+    const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
+
+    // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32)
+    float gn[J];
+#pragma unroll
+    for (int i = 0; i < J; ++i) gn[i] = a[i];                          // goals <- action (manytor.py:184)
+    if ((P.flags & kAutoReset) && done && valid) {
+        atomicAdd(P.stats + 1, 1ull);
+        atomicAdd(P.stats + 2, term ? 1ull : 0ull);
+        atomicAdd(P.stats + 3, (unsigned long long)(long long)total);
+        atomicAdd(P.stats + 4, (unsigned long long)eplen);
+        atomicAdd(P.stats + 5, (unsigned long long)(x - __popc(alive1)));
+        atomicAdd(P.stats + 6, (unsigned long long)gsteps);
+        const uint32_t ep = P.episode[env];                            // resets so far
+        P.episode[env] = ep + 1u;
+        float *grow = P.points + env * rowlen;
+        Frames f0;
+        f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
+        f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
+        for (int pt = 0; pt < x; ++pt) {
+            float px, py, pz;
+            if (P.obj_stream) {
+                const float *src = P.obj_stream + (((long long)(ep % (uint32_t)P.obj_sets) * P.n + env) * x + pt) * 3;
+                px = src[0]; py = src[1]; pz = src[2];
+            } else {
+                sample_point(P, P.env_id_base + env, ep, pt, px, py, pz);
+            }
+            grow[pt * 3 + 0] = px; grow[pt * 3 + 1] = py; grow[pt * 3 + 2] = pz;
+            if (WOBS && (P.flags & kObsAfterReset)) {
+                one_objective<true>(px, py, pz, f0, P.catch_tol, true);
+                row[pt * 3 + 0] = px; row[pt * 3 + 1] = py; row[pt * 3 + 2] = pz;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < J; ++i) gn[i] = 0.f;
+        alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
+        total = 0.f;
+        eplen = 0u;
+        gsteps = 0u;
+    }
+
+    // 7. write back: state (coalesced), then the observation tile by one bulk store
+    if (J == 4) {
+        *reinterpret_cast<float4 *>(P.goals + env * 4) = make_float4(gn[0], gn[1], gn[2], gn[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < J; ++i) P.goals[env * J + i] = gn[i];
+    }
+    P.alive[env] = alive1;
+    P.total_reward[env] = total;
+    P.counters[env] = eplen | (gsteps << 16);
+    if (valid) {
+        P.reward[env] = rew;
+        P.done[env] = done;
+        if (P.joints) {
+#pragma unroll
+            for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
+        }
+    }
+    if (WOBS) {
+        if (full) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(P.obs + env0 * rowlen, tile_s, tile_bytes);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+        } else if (valid) {
+            float *dst = P.obs + env * rowlen;
+            for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
+        }
+    }
+}
+
+}  // namespace mt

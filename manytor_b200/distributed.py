@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing: environments shard contiguously across ranks, one process
+per GPU, NO per-step collective (envs never interact, manytor.py:115-122); the
+only exchange is one all-reduce (NCCL over NVLink on GPUs, gloo in CPU tests) of
+the MT_STATS_WORDS episode-statistics vector at the end of a rollout.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._lib import STATS_FIELDS
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of [0, n_total): returns (first global env id, count) of `rank`.
+    Global ids key the RNG, so results do not depend on the shard count."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(int(n_total), world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """Join the process group torchrun described (RANK/WORLD_SIZE/LOCAL_RANK/MASTER_*);
+    returns (rank, world, local_rank).  No-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-shard statistics vector over all ranks (in place) -- the single
+    collective of a multi-GPU rollout."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def stats_dict(stats: torch.Tensor) -> dict:
+    v = stats.detach().cpu().tolist()
+    return {k: int(v[i]) for i, k in enumerate(STATS_FIELDS)}
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Max of a per-rank scalar (device timings are reported as the slowest rank)."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,397 @@
+"""CUDA path vs the CPU oracle and the reference's golden traces (-m gpu).
+
+Every call goes through the C ABI (manytor_b200._lib -> libmanytor_b200.so)."""
+import numpy as np
+import pytest
+
+from oracle import OracleEnvs, REFERENCE_ARM, UR5_ARM, sample_points_reference_stream
+from oracle.philox import device_actions
+
+from parity import Report, alive_bits_to_matrix, compare_step, lockstep
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["single_x10_seed0", "multi_3x2_x7_seed1", "batch32_x10_seed2", "batch16_x2_seed3", "batch8_x10_seed4"]
+
+
+@pytest.fixture(scope="module")
+def mt():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import manytor_b200
+    manytor_b200.load_library()
+    return manytor_b200
+
+
+def ref_points(n, x, seed):
+    st = np.random.get_state()
+    np.random.seed(seed)
+    pts = np.stack([sample_points_reference_stream(x) for _ in range(n)])
+    np.random.set_state(st)
+    return pts
+
+
+# --------------------------------------------------------------------------
+# golden traces of the unmodified reference
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_trace(mt, golden, name):
+    g = golden(name)
+    x = int(g["x"])
+    T, n = g["reward"].shape
+    env = mt.BatchedEnvs(n, x, device=0)
+    ora = OracleEnvs(n, x)
+    rep = Report()
+    for t in range(T):
+        m = ~np.isnan(g["fresh"][t, :, 0, 0])
+        if m.any():
+            fresh = np.nan_to_num(g["fresh"][t])
+            ora.reset(mask=m, points=fresh)
+            env.reset(mask=m)
+            env.set_points(fresh, mask=m)
+            if t == 0:
+                o0 = env.observe().cpu().numpy()
+                np.testing.assert_allclose(o0[:, 0::3], g["obs0"][:, 0::3], atol=2e-3)
+        alive_before, points_before = ora.alive.copy(), ora.points.copy()
+        obs, rew, done, jn = (o.cpu().numpy() for o in env.step(g["actions"][t].astype(np.float32), joints=True))
+        r = ora.step(g["actions"][t])
+        # the oracle equals the reference on this trace (tests/test_oracle_golden.py)
+        assert np.array_equal(r.reward, g["reward"][t]) and np.array_equal(r.done, g["done"][t])
+        dev_alive = alive_bits_to_matrix(env.get_state()["alive"].cpu().numpy(), x)
+        bad = compare_step(rep, REFERENCE_ARM, ora, r, points_before, alive_before, obs, rew, done, dev_alive, jn)
+        np.testing.assert_allclose(jn, g["joints"][t], atol=5.6e-4)
+        if bad.any():
+            env.set_state(goals=ora.goals, alive=ora.alive, total_reward=ora.total_reward, mask=bad)
+    print(name, rep.summary())
+    assert rep.ok(), rep.notes[:5]
+    assert rep.near_threshold <= max(2, rep.env_steps // 500)
+
+
+# --------------------------------------------------------------------------
+# BASELINE.json config 2: 4096 lock-step envs, x = 10, fp32 parity vs numpy
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("steps", [1000])
+def test_config2_4096_envs(mt, steps):
+    n, x = 4096, 10
+    env = mt.BatchedEnvs(n, x, device=0)
+    ora = OracleEnvs(n, x)
+    pts = ref_points(n, x, seed=11)                      # objectives from the reference's RNG, uploaded
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(12)
+    refresh = np.random.RandomState(13)
+
+    def fresh(t, done):
+        # refresh stream for envs that collected everything (reference distribution, vectorised)
+        out = np.zeros((n, x, 3))
+        for i in np.nonzero(done)[0]:
+            k = 0
+            while k < x:
+                c = refresh.uniform(-51.3, 51.3, size=3)
+                if c[2] >= 0 and np.sqrt((c ** 2).sum()) <= 51.3:
+                    out[i, k] = c
+                    k += 1
+        return out
+
+    rep = lockstep(env, ora, REFERENCE_ARM, lambda t: rng.randint(-180, 180, size=(n, 4)), steps, on_done=fresh)
+    print("config2", rep.summary())
+    assert rep.ok(), rep.notes[:5]
+    assert rep.max_joint_err < 5.56e-4
+    assert rep.near_threshold < rep.env_steps * 2e-4
+
+
+def test_generic_chain_on_reference_arm(mt):
+    """The pluggable DH-chain kernel (fk_mode=1) must agree with the oracle on the reference arm too."""
+    n, x = 512, 10
+    env = mt.BatchedEnvs(n, x, device=0, fk_mode=1)
+    ora = OracleEnvs(n, x)
+    pts = ref_points(n, x, seed=3)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(4)
+    rep = lockstep(env, ora, REFERENCE_ARM, lambda t: rng.uniform(-180, 180, size=(n, 4)), 60)
+    print("generic-on-ref", rep.summary())
+    assert rep.ok(), rep.notes[:5]
+
+
+def test_config5_ur5_six_dof(mt):
+    """BASELINE.json config 5: 6-DOF UR5-style chain, x = 20."""
+    n, x = 1024, 20
+    env = mt.BatchedEnvs(n, x, arm=mt.UR5_ARM, device=0)
+    ora = OracleEnvs(n, x, spec=UR5_ARM)
+    rng = np.random.RandomState(21)
+    env.reset()
+    pts = env.get_points(zero_dead=False).cpu().numpy().astype(np.float64)   # on-device sampler, downloaded
+    assert (np.linalg.norm(pts, axis=-1) <= UR5_ARM.radius * (1 + 1e-6)).all() and (pts[..., 2] >= 0).all()
+    ora.reset(points=pts)
+    rep = lockstep(env, ora, UR5_ARM, lambda t: rng.randint(-180, 180, size=(n, 6)), 80)
+    print("ur5", rep.summary())
+    assert rep.ok(), rep.notes[:5]
+
+
+@pytest.mark.parametrize("n,x", [(1, 10), (33, 1), (95, 7), (64, 32), (100, 5), (31, 20), (257, 4)])
+def test_ragged_sizes(mt, n, x):
+    """Tail tiles (N not a multiple of 32), single env, X = 1 / odd / 32 (max)."""
+    env = mt.BatchedEnvs(n, x, device=0)
+    ora = OracleEnvs(n, x)
+    pts = ref_points(n, x, seed=n + x)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(n)
+    rep = lockstep(env, ora, REFERENCE_ARM, lambda t: rng.randint(-180, 180, size=(n, 4)), 25)
+    assert rep.ok(), rep.notes[:5]
+
+
+def test_float_actions_and_wide_range(mt):
+    """Non-integer targets and targets far outside [-180, 180) (exact half-turn reduction)."""
+    n, x = 256, 10
+    env = mt.BatchedEnvs(n, x, device=0)
+    ora = OracleEnvs(n, x)
+    pts = ref_points(n, x, seed=8)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(9)
+
+    def acts(t):
+        a = rng.uniform(-720, 720, size=(n, 4))
+        return np.float32(a).astype(np.float64)          # the device sees fp32 inputs; give the oracle the same
+    rep = lockstep(env, ora, REFERENCE_ARM, acts, 40)
+    assert rep.ok(), rep.notes[:5]
+
+
+def test_terminate_on_ground_option(mt):
+    n, x = 128, 10
+    env = mt.BatchedEnvs(n, x, device=0, terminate_on_ground=True)
+    ora = OracleEnvs(n, x, terminate_on_ground=True)
+    pts = ref_points(n, x, seed=5)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(6)
+    rep = lockstep(env, ora, REFERENCE_ARM, lambda t: rng.randint(-180, 180, size=(n, 4)), 10)
+    assert rep.ok(), rep.notes[:5]
+
+
+# --------------------------------------------------------------------------
+# on-device auto-reset with an uploaded objective stream (no host round trip)
+# --------------------------------------------------------------------------
+def test_auto_reset_with_objective_stream(mt):
+    import torch
+    n, x, sets, steps, horizon = 512, 2, 6, 400, 60
+    rs = np.random.RandomState(31)
+    stream = np.zeros((sets, n, x, 3))
+    for s in range(sets):
+        v = rs.normal(size=(n, x, 3))
+        v /= np.linalg.norm(v, axis=-1, keepdims=True)
+        v[..., 2] = np.abs(v[..., 2])
+        stream[s] = v * (51.3 * rs.uniform(0, 1, size=(n, x, 1)) ** (1 / 3))
+    stream = np.float32(stream).astype(np.float64)
+    env = mt.BatchedEnvs(n, x, device=0, auto_reset=True, horizon=horizon)
+    env.set_objective_stream(stream)
+    env.reset()                                           # takes set 0
+    ora = OracleEnvs(n, x)
+    ora.reset(points=stream[0])
+    episode = np.ones(n, dtype=np.int64)                  # resets so far
+    rng = np.random.RandomState(32)
+    rep = Report()
+    stats = dict(episodes=0, terminated=0, reward_sum=0, length_sum=0, catches=0)
+    slack, structural = 0, False
+    for t in range(steps):
+        act = rng.randint(-180, 180, size=(n, 4)).astype(np.float64)
+        alive_before, points_before = ora.alive.copy(), ora.points.copy()
+        obs, rew, done, jn = (o.cpu().numpy() for o in env.step(act.astype(np.float32), joints=True))
+        r = ora.step(act)
+        trunc = (ora.ep_len >= horizon) & ~r.done
+        ended = r.done | trunc
+        # device state after its in-kernel reset: rebuild what the pre-reset alive mask was from `done`
+        st = env.get_state()
+        dev_alive_after = alive_bits_to_matrix(st["alive"].cpu().numpy(), x)
+        dev_alive = np.where(ended[:, None], r.alive, dev_alive_after)   # ended envs were reset on device
+        bad = compare_step(rep, REFERENCE_ARM, ora, r, points_before, alive_before, obs, rew, done, dev_alive, jn)
+        assert rep.ok(), rep.notes[:5]
+        if bad.any():
+            # near-threshold flips (already classified by compare_step).  A ground flip only moves the
+            # reward: re-sync total_reward and keep going; a catch/done flip forks the episode structure.
+            forked = (((done & 1).astype(bool) != r.done) | (dev_alive != r.alive).any(axis=1)) & bad
+            if forked.any():
+                structural = True
+                break
+            slack += 2 * int((bad & ended).sum())
+            if (bad & ~ended).any():
+                env.set_state(total_reward=ora.total_reward, mask=bad & ~ended)
+        assert np.array_equal((done & 2).astype(bool), trunc)
+        if ended.any():
+            stats["episodes"] += int(ended.sum())
+            stats["terminated"] += int(r.done.sum())
+            stats["reward_sum"] += int(ora.total_reward[ended].sum())
+            stats["length_sum"] += int(ora.ep_len[ended].sum())
+            stats["catches"] += int((x - r.alive[ended].sum(axis=1)).sum())
+            fresh = stream[episode % sets, np.arange(n)]
+            ora.reset(mask=ended, points=fresh)
+            episode[ended] += 1
+            assert np.all(dev_alive_after[ended]) and np.all(st["goals"].cpu().numpy()[ended] == 0)
+            np.testing.assert_array_equal(env.get_points(zero_dead=False).cpu().numpy()[ended],
+                                          np.float32(fresh[ended]))
+    s = env.stats()
+    print("auto-reset", rep.summary(), s)
+    assert rep.ok(), rep.notes[:5]
+    if not structural:
+        assert s["env_steps"] == n * steps
+        for k, v in stats.items():
+            assert abs(s[k] - v) <= (slack if k == "reward_sum" else 0), (k, s[k], v)
+        assert s["live_reward_sum"] == int(ora.total_reward.sum())
+        assert stats["episodes"] > n      # every env ended at least once (horizon 60 over 400 steps)
+
+
+# --------------------------------------------------------------------------
+# on-device RNG streams
+# --------------------------------------------------------------------------
+def test_sample_actions_match_philox_oracle(mt):
+    n = 1000
+    for J, arm in ((4, mt.REFERENCE_ARM), (6, mt.UR5_ARM)):
+        env = mt.BatchedEnvs(n, 3, arm=arm, device=0, seed=0x1234567890ABCDEF, env_id_base=(1 << 33) + 5)
+        env.reset()
+        a0 = env.sample_actions().cpu().numpy()
+        exp0 = device_actions(0x1234567890ABCDEF, (1 << 33) + 5 + np.arange(n), 0, J)
+        np.testing.assert_array_equal(a0.astype(np.int64), exp0)
+        assert a0.min() >= -180 and a0.max() <= 179
+        env.step(a0)                                      # advances the step index
+        a1 = env.sample_actions().cpu().numpy()
+        np.testing.assert_array_equal(a1.astype(np.int64), device_actions(0x1234567890ABCDEF, (1 << 33) + 5 + np.arange(n), 1, J))
+
+
+def test_rollout_random_equals_step_of_sampled_actions(mt):
+    import torch
+    n, x, k = 4096 + 17, 10, 12
+    a = mt.BatchedEnvs(n, x, device=0, seed=7, auto_reset=True, horizon=5)
+    b = mt.BatchedEnvs(n, x, device=0, seed=7, auto_reset=True, horizon=5)
+    a.reset(); b.reset()
+    for _ in range(k):
+        oa, ra, da = a.rollout_random(1)
+        ob, rb, db = b.step(b.sample_actions())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
+    sa, sb = a.get_state(), b.get_state()
+    for key in sa:
+        assert torch.equal(sa[key], sb[key]), key
+    assert torch.equal(a.get_points(False), b.get_points(False))
+    assert a.stats() == b.stats()
+    # without observation write the state evolves identically
+    c = mt.BatchedEnvs(n, x, device=0, seed=7, auto_reset=True, horizon=5)
+    c.reset()
+    c.rollout_random(k, write_obs=False)
+    sc = c.get_state()
+    for key in sa:
+        assert torch.equal(sa[key], sc[key]), key
+
+
+def test_shard_invariance(mt):
+    """N envs on one handle == the same envs split over two handles (global env ids key the RNG)."""
+    import torch
+    n, x, k = 3000, 10, 30
+    whole = mt.BatchedEnvs(n, x, device=0, seed=99, auto_reset=True, horizon=7)
+    cut = 1234
+    parts = [mt.BatchedEnvs(cut, x, device=0, seed=99, auto_reset=True, horizon=7, env_id_base=0),
+             mt.BatchedEnvs(n - cut, x, device=0, seed=99, auto_reset=True, horizon=7, env_id_base=cut)]
+    whole.reset()
+    for p in parts:
+        p.reset()
+    for _ in range(k):
+        ow, rw, dw = whole.rollout_random(1)
+        outs = [p.rollout_random(1) for p in parts]
+        assert torch.equal(ow, torch.cat([o[0] for o in outs]))
+        assert torch.equal(rw, torch.cat([o[1] for o in outs]))
+        assert torch.equal(dw, torch.cat([o[2] for o in outs]))
+    sw = whole.stats()
+    sp = [p.stats() for p in parts]
+    for key in sw:
+        assert sw[key] == sp[0][key] + sp[1][key], key
+
+
+def test_objective_sampler_distribution(mt):
+    """On-device refresh must follow the reference's law (manytor.py:228-239): uniform in the
+    upper half ball -> radius CDF (r/R)^3, z >= 0, azimuth uniform, cos(polar) uniform."""
+    from scipy import stats as sst
+    n, x, R = 40000, 10, 51.3
+    env = mt.BatchedEnvs(n, x, device=0, seed=5)
+    env.reset()
+    p = env.get_points(zero_dead=False).cpu().numpy().astype(np.float64).reshape(-1, 3)
+    r = np.linalg.norm(p, axis=1)
+    assert (p[:, 2] >= 0).all() and (r <= R * (1 + 1e-6)).all()
+    sub = slice(0, 50000)
+    assert sst.kstest((r[sub] / R) ** 3, "uniform").pvalue > 1e-3
+    assert sst.kstest((np.arctan2(p[sub, 1], p[sub, 0]) + np.pi) / (2 * np.pi), "uniform").pvalue > 1e-3
+    assert sst.kstest(p[sub, 2] / r[sub], "uniform").pvalue > 1e-3
+    # same law as the reference's rejection sampler
+    ref = np.stack([sample_points_reference_stream(1)[0] for _ in range(4000)])
+    assert sst.ks_2samp(np.linalg.norm(ref, axis=1), r[:20000]).pvalue > 1e-3
+    assert sst.ks_2samp(ref[:, 0], p[:20000, 0]).pvalue > 1e-3
+    assert sst.ks_2samp(ref[:, 2], p[:20000, 2]).pvalue > 1e-3
+    # a second reset draws new objectives; another seed draws different ones
+    env.reset()
+    p2 = env.get_points(zero_dead=False).cpu().numpy().reshape(-1, 3)
+    assert np.abs(p2 - p).max() > 1.0
+
+
+# --------------------------------------------------------------------------
+# API behaviour
+# --------------------------------------------------------------------------
+def test_errors_are_loud(mt):
+    import torch
+    env = mt.BatchedEnvs(64, 10, device=0)
+    with pytest.raises(mt.MantorLibraryError, match="before mt_reset"):
+        env.step(np.zeros((64, 4), dtype=np.float32))       # the reference raises IndexError here
+    with pytest.raises(mt.MantorLibraryError):
+        mt.BatchedEnvs(64, 33, device=0)                     # n_obj > MT_MAX_OBJ
+    with pytest.raises(mt.MantorLibraryError):
+        mt.BatchedEnvs(0, 10, device=0)
+    with pytest.raises(mt.MantorLibraryError):
+        mt.BatchedEnvs(8, 10, device=0, fk_mode=2, arm=mt.UR5_ARM)
+    with pytest.raises(mt.MantorLibraryError):
+        mt.BatchedEnvs(8, 10, device="cpu")
+
+
+def test_step_host_equals_device_step(mt):
+    import torch
+    n, x = 5000, 10
+    a = mt.BatchedEnvs(n, x, device=0, seed=3)
+    b = mt.BatchedEnvs(n, x, device=0, seed=3)
+    a.reset(); b.reset()
+    rng = np.random.RandomState(1)
+    for _ in range(5):
+        act = rng.randint(-180, 180, size=(n, 4)).astype(np.float32)
+        oa, ra, da = a.step(act)
+        ob, rb, db = b.step_host(act)
+        np.testing.assert_array_equal(oa.cpu().numpy(), ob)
+        np.testing.assert_array_equal(ra.cpu().numpy(), rb)
+        np.testing.assert_array_equal(da.cpu().numpy(), db)
+
+
+def test_state_roundtrip_and_dead_points(mt):
+    n, x = 77, 10
+    env = mt.BatchedEnvs(n, x, device=0, seed=3)
+    env.reset()
+    rng = np.random.RandomState(2)
+    goals = rng.uniform(-180, 180, size=(n, 4)).astype(np.float32)
+    alive = rng.rand(n, x) > 0.4
+    tot = rng.randint(-50, 5, size=n).astype(np.float32)
+    ep = rng.randint(0, 1000, size=n).astype(np.int32)
+    env.set_state(goals=goals, alive=alive, total_reward=tot, ep_len=ep)
+    st = env.get_state()
+    np.testing.assert_array_equal(st["goals"].cpu().numpy(), goals)
+    np.testing.assert_array_equal(alive_bits_to_matrix(st["alive"].cpu().numpy(), x), alive)
+    np.testing.assert_array_equal(st["total_reward"].cpu().numpy(), tot)
+    np.testing.assert_array_equal(st["ep_len"].cpu().numpy(), ep)
+    raw = env.get_points(zero_dead=False).cpu().numpy()
+    z = env.get_points(zero_dead=True).cpu().numpy()
+    assert np.all(z[~alive] == 0) and np.array_equal(z[alive], raw[alive])     # manytor.py:148
+    obs = env.observe().cpu().numpy().reshape(n, x, 3)
+    assert np.all(obs[~alive] == 0) and np.all(obs[alive][:, 0] > 0)
+    f = env.fetch_env(5)
+    np.testing.assert_array_equal(f["alives"], alive[5])
+    np.testing.assert_array_equal(f["goals"], goals[5])
+    from oracle.manytor_oracle import joints_coordinates
+    np.testing.assert_allclose(f["joints_coordinates"], joints_coordinates(goals[5].astype(np.float64)), atol=5.6e-4)

@@ -1,0 +1,69 @@
+"""Host-side logic that needs no GPU: sharding arithmetic and the one collective
+(statistics all-reduce), exercised with world_size=2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from manytor_b200 import distributed as mtd
+from manytor_b200._lib import MT_STATS_WORDS, STATS_FIELDS
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 8, 1 << 20, (1 << 23) + 5):
+        for world in (1, 2, 3, 4, 8):
+            spans = [mtd.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0
+            for a, b in zip(spans, spans[1:]):
+                assert a[0] + a[1] == b[0]
+            assert spans[-1][0] + spans[-1][1] == n
+            sizes = [s[1] for s in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        mtd.shard_range(10, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = mtd.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    base, count = mtd.shard_range(n_total, rank, world)
+    # a fake per-shard statistics vector in the layout of mt_stats (include/manytor_b200.h)
+    stats = torch.tensor([count * 10, count // 3, count // 7, -count, count * 5, count * 2, count, base],
+                         dtype=torch.int64)
+    assert stats.numel() == MT_STATS_WORDS
+    mtd.allreduce_stats(stats)
+    t = mtd.max_over_ranks(1.0 + rank)
+    out[rank] = (stats.tolist(), t, base, count)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_stats_allreduce_world2_gloo():
+    world, n_total = 2, 1001
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_total, out), nprocs=world, join=True)
+    counts = [out[r][3] for r in range(world)]
+    bases = [out[r][2] for r in range(world)]
+    assert sum(counts) == n_total and bases == [0, counts[0]]
+    expect = [sum(c * 10 for c in counts), sum(c // 3 for c in counts), sum(c // 7 for c in counts),
+              -n_total, n_total * 5, n_total * 2, n_total, sum(bases)]
+    for r in range(world):
+        assert out[r][0] == expect            # every rank holds the global sum
+        assert out[r][1] == 2.0               # max over ranks of the per-rank time
+    assert mtd.stats_dict(torch.tensor(expect))["env_steps"] == expect[0]
+    assert list(mtd.stats_dict(torch.tensor(expect))) == list(STATS_FIELDS)
