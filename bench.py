@@ -249,11 +249,17 @@ def run_gpu(args) -> None:
     def step_fn(i):
         env.step(actions[i % n_act])
 
+    # bring clocks / power state to steady load before timing (untimed, same kernel)
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < args.clock_warm_s:
+        for i in range(200):
+            step_fn(i)
+        torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
     for i in range(W):
         step_fn(i)
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-    if sampler:
-        sampler.start()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     l0 = env.launch_count
     e0.record(stream)
@@ -264,8 +270,20 @@ def run_gpu(args) -> None:
     mtd.allreduce_stats(st)                       # ... one NCCL all-reduce (config 4)
     e2.record(stream)
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
+    launches_timed = env.launch_count - l0
+    timed_ms_local = e0.elapsed_time(e2)
+    # K steps last only a few ms, far below nvidia-smi's sampling period: keep the same step
+    # loop running (untimed) so the clock sampler sees the load the timed region ran under
+    t_cont = time.perf_counter()
+    while sampler and time.perf_counter() - t_cont < args.clock_probe_s:
+        for i in range(200):
+            step_fn(i)
+        torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    launches = env.launch_count - l0
+    if clocks is not None:
+        clocks["note"] = (f"sampled every 50 ms from just before the warm-up steps, through the {timed_ms_local:.1f} ms "
+                          f"timed region, and over a {args.clock_probe_s:.1f} s untimed continuation of the same step loop")
+    launches = launches_timed
     ms_total = mtd.max_over_ranks(e0.elapsed_time(e2), dev)
     ms_kernels = mtd.max_over_ranks(e0.elapsed_time(e1), dev)
     stats = mtd.stats_dict(st)
@@ -277,10 +295,11 @@ def run_gpu(args) -> None:
 
     # ---- other modes (short), for the roofline discussion -------------------------------
     modes = {}
-    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=True), K, 3)
-    modes["rollout_random_in_kernel_actions"] = {"env_steps_per_s": n * K / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, True)}
-    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=False), K, 3)
-    modes["rollout_random_no_obs_write"] = {"env_steps_per_s": n * K / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, False)}
+    KM = min(K, 500)
+    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=True), KM, 3)
+    modes["rollout_random_in_kernel_actions"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, True)}
+    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=False), KM, 3)
+    modes["rollout_random_no_obs_write"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, False)}
     for m in modes.values():
         m["hbm_gbs"] = m["env_steps_per_s"] * m["bytes_per_env_step"] / 1e9
         m["frac_of_peak"] = m["hbm_gbs"] / peak
@@ -340,8 +359,10 @@ def run_gpu(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--clock-warm-s", type=float, default=1.0, help="untimed seconds of the step loop before warm-up")
+    ap.add_argument("--clock-probe-s", type=float, default=1.0, help="untimed continuation for the clock sampler")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--burn-in", type=int, default=HORIZON,

@@ -205,7 +205,11 @@ class BatchedEnvs:
         done (N,) u8 [, joints (N,J,3)]) -- views of buffers this object reuses
         on the next step.
         """
-        a = self._as_dev(actions, torch.float32, (self.n, self.j))
+        if (isinstance(actions, torch.Tensor) and actions.is_cuda and actions.dtype == torch.float32
+                and actions.is_contiguous() and actions.numel() == self.n * self.j):
+            a = actions                                    # fast path: already the device layout
+        else:
+            a = self._as_dev(actions, torch.float32, (self.n, self.j))
         self._out_buffers(write_obs, joints)
         _lib.check(self._lib.mt_step(self._h, self._p(a), self._p(self._obs if write_obs else None),
                                      self._p(self._reward), self._p(self._done),

@@ -448,8 +448,9 @@ __global__ void r_theta_kernel(const float *v1, const float *v2, long long m, fl
     if (i >= m) return;
     float dx = fabsf(v1[i * 3] - v2[i * 3]), dy = fabsf(v1[i * 3 + 1] - v2[i * 3 + 1]),
           dz = fabsf(v1[i * 3 + 2] - v2[i * 3 + 2]);
-    out[i * 2] = atan2_deg_pos(dx, dy);
-    out[i * 2 + 1] = atan2_deg_pos(fast_sqrt(fmaf(dx, dx, dy * dy)), dz);
+    const float h2 = fmaf(dx, dx, dy * dy), h = fast_sqrt(h2);
+    out[i * 2] = atan2_deg_pos(dx, dy, h);
+    out[i * 2 + 1] = atan2_deg_pos(h, dz, fast_sqrt(fmaf(dz, dz, h2)));
 }
 
 // ----------------------------------------------------------------------------

@@ -28,24 +28,41 @@ __device__ __forceinline__ void sincos_deg(float x, float &s, float &c) {
     c = ((q + 1) & 2) ? -cc : cc;
 }
 
+// sin/cos of a SMALL angle in degrees, |x| <= 45: quadrant 0 of the reduction
+// above, so no rint / swap / sign logic (used for the per-sub-pose half steps).
+__device__ __forceinline__ void sincos_deg_small(float x, float &s, float &c) {
+    const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f;
+    float r = fmaf(x, inv_lo, x * inv_hi);
+    float u = r * r;
+    s = fmaf(fmaf(fmaf(-0.58907866f, u, 2.5497673f), u, -5.1677079f), u, 3.14159274f) * r;
+    c = fmaf(fmaf(fmaf(fmaf(0.23132971f, u, -1.33504462f), u, 4.05870724f), u, -4.93480206f), u, 1.0f);
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ------------------------------------------------------------------- atan2
 // degrees(atan2(y, x)) for y >= 0, x >= 0 (the reference only ever passes
-// absolute values, manytor.py:18-21); atan2(0, 0) = 0 like math.atan2.
-__device__ __forceinline__ float atan2_deg_pos(float y, float x) {
-    float mx = fmaxf(x, y), mn = fminf(x, y);
-    float t = __fdividef(mn, mx);
-    t = (mx == 0.0f) ? 0.0f : t;
+// absolute values, manytor.py:18-21), given hyp = sqrt(x^2 + y^2), which the
+// caller already has.  Half-angle form: atan2(y, x) = 2 atan(y / (x + hyp));
+// the argument lies in [0, 1] over the whole quadrant, so there is no
+// min/max/select; x + hyp adds two non-negative numbers (no cancellation).
+// atan2(0, 0) = 0 like math.atan2.
+__device__ __forceinline__ float atan2_deg_pos(float y, float x, float hyp) {
+    float t = y * fast_rcp(fmaxf(x + hyp, 1e-30f));
     float s = t * t;
-    float p = -0.27388057f;
-    p = fmaf(p, s, 1.40695274f);
-    p = fmaf(p, s, -3.43219686f);
-    p = fmaf(p, s, 5.6967206f);
-    p = fmaf(p, s, -8.03824425f);
-    p = fmaf(p, s, 11.4427519f);
-    p = fmaf(p, s, -19.0978832f);
-    p = fmaf(p, s, 57.2957726f);
-    float r = p * t;
-    return (y > x) ? 90.0f - r : r;
+    float p = -0.54776114f;
+    p = fmaf(p, s, 2.81390548f);
+    p = fmaf(p, s, -6.86439371f);
+    p = fmaf(p, s, 11.3934412f);
+    p = fmaf(p, s, -16.0764885f);
+    p = fmaf(p, s, 22.8855038f);
+    p = fmaf(p, s, -38.1957664f);
+    p = fmaf(p, s, 114.591545f);
+    return p * t;
 }
 
 __device__ __forceinline__ float fast_sqrt(float x) {

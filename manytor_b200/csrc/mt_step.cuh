@@ -92,10 +92,33 @@ __device__ __forceinline__ void rot_back(float &c, float &s, float cd, float sd)
 //   ee     = elbow + 27 (s3 (c0 c1 c2 - s0 s2) + c3 c0 s1,
 //                        s3 (s0 c1 c2 + c0 s2) + c3 s0 s1,
 //                        c3 c1 - s3 s1 c2)
-// (theta3 before its -pi/2 offset).  Only the z components are needed at the 24
-// interior sub-poses; they depend on theta1..3 only and the route is linear in
-// angle, so their sin/cos follow by one plane rotation per joint per sub-pose,
-// run backwards from the exact final pose.
+// (theta3 before its -pi/2 offset).  Only the two z values are needed at the 24
+// interior sub-poses (manytor.py:191), and with A = th1 + th3, B = th1 - th3
+//   elbow_z - 4.3 = 24.3 cos th1                                  =: u1
+//   ee_z    - 4.3 = u1 + uA + uB + cos th2 (uA - uB),   uA = 13.5 cos A, uB = 13.5 cos B
+// The route is linear in angle (np.linspace, manytor.py:182), so u1, cos th2, uA,
+// uB are four sampled cosines.  Each is advanced by Reinsch's recurrence
+//   x <- x + d;  d <- d - 4 sin^2(delta/2) x
+// (2 FMA-class ops per value per sub-pose, error growth linear in the step
+// count), run backwards from the exact final pose: 13 instructions per sub-pose
+// instead of 3 plane rotations + products.  tools/emulate_subpose.py compares it
+// with fp64: max |dz| 3.5e-5 over 4e5 random steps, no ground-flag flips.
+struct CosSeq {
+    float x, d, na;  // value, backward difference, -4 sin^2(delta/2)
+    // amp * cos(theta - k * delta), k = 0, 1, ...; (sh, ch) = sin/cos(delta / 2)
+    __device__ __forceinline__ void init(float amp, float cth, float sth, float sh, float ch) {
+        float t = sh + sh;
+        na = -(t * t);                    // -4 sh^2
+        x = amp * cth;
+        // amp (cos(theta - delta) - cos theta) = amp sin(theta) sin(delta) - 2 sh^2 x
+        d = fmaf(amp * sth, t * ch, 0.5f * na * x);
+    }
+    __device__ __forceinline__ void back() {
+        x += d;
+        d = fmaf(na, x, d);
+    }
+};
+
 __device__ __forceinline__ void ref_arm(const float *g, const float *a, int substeps, float inv_div, Frames &f,
                                         float *jout /* 12 floats or nullptr */) {
     float s0, c0, s1, c1, s2, c2, s3, c3;
@@ -123,18 +146,40 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
         jout[9] = tx; jout[10] = ty; jout[11] = tz;
     }
     float zmin = fminf(ez, tz);
-    float sd1, cd1, sd2, cd2, sd3, cd3;
-    sincos_deg((a[1] - g[1]) * inv_div, sd1, cd1);
-    sincos_deg((a[2] - g[2]) * inv_div, sd2, cd2);
-    sincos_deg((a[3] - g[3]) * inv_div, sd3, cd3);
+    if (substeps > 1) {
+        // half steps in degrees; the small-angle sin/cos holds for |half step| <= 45, i.e. any
+        // target within +-2160 degrees of the current pose at 25 sub-poses (else: general path)
+        const float hs = 0.5f * inv_div;
+        const float h1 = (a[1] - g[1]) * hs, h2 = (a[2] - g[2]) * hs, h3 = (a[3] - g[3]) * hs;
+        float sh1, ch1, sh2, ch2, sh3, ch3;
+        const bool small = fmaxf(fmaxf(fabsf(h1), fabsf(h2)), fabsf(h3)) <= 45.0f;
+        if (__all_sync(__activemask(), small)) {
+            sincos_deg_small(h1, sh1, ch1);
+            sincos_deg_small(h2, sh2, ch2);
+            sincos_deg_small(h3, sh3, ch3);
+        } else {
+            sincos_deg(h1, sh1, ch1);
+            sincos_deg(h2, sh2, ch2);
+            sincos_deg(h3, sh3, ch3);
+        }
+        // A = th1 + th3, B = th1 - th3 and their half steps by angle addition
+        const float cA = fmaf(c1, c3, -(s1 * s3)), sA = fmaf(s1, c3, c1 * s3);
+        const float cB = fmaf(c1, c3, s1 * s3), sB = fmaf(s1, c3, -(c1 * s3));
+        const float chA = fmaf(ch1, ch3, -(sh1 * sh3)), shA = fmaf(sh1, ch3, ch1 * sh3);
+        const float chB = fmaf(ch1, ch3, sh1 * sh3), shB = fmaf(sh1, ch3, -(ch1 * sh3));
+        CosSeq q1, q2, qA, qB;
+        q1.init(L1, c1, s1, sh1, ch1);
+        q2.init(1.0f, c2, s2, sh2, ch2);
+        qA.init(0.5f * L2, cA, sA, shA, chA);
+        qB.init(0.5f * L2, cB, sB, shB, chB);
+        float m = 3.0e38f;
 #pragma unroll 4
-    for (int p = 1; p < substeps; ++p) {
-        rot_back(c1, s1, cd1, sd1);
-        rot_back(c2, s2, cd2, sd2);
-        rot_back(c3, s3, cd3, sd3);
-        float ze = fmaf(L1, c1, H);
-        float zt = fmaf(L2, fmaf(c3, c1, -((s3 * s1) * c2)), ze);
-        zmin = fminf(zmin, fminf(ze, zt));
+        for (int p = 1; p < substeps; ++p) {
+            q1.back(); q2.back(); qA.back(); qB.back();
+            float t = fmaf(q2.x, qA.x - qB.x, q1.x + (qA.x + qB.x));
+            m = fminf(m, fminf(q1.x, t));
+        }
+        zmin = fminf(zmin, m + H);
     }
     f.zmin = zmin;
 }
@@ -221,8 +266,8 @@ __device__ __forceinline__ bool one_objective(float &px, float &py, float &pz, c
         float h2 = fmaf(dx, dx, dy * dy);
         float dist = fast_sqrt(fmaf(dz, dz, h2));
         float h = fast_sqrt(h2);
-        float r = atan2_deg_pos(dx, dy);
-        float th = atan2_deg_pos(h, dz);
+        float r = atan2_deg_pos(dx, dy, h);
+        float th = atan2_deg_pos(h, dz, dist);
         px = alive ? dist : 0.0f;
         py = alive ? r : 0.0f;
         pz = alive ? th : 0.0f;
