@@ -57,6 +57,7 @@ struct mt_env {
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;
+    int num_sms = 0;
     const float *obj_stream = nullptr;
     int32_t obj_sets = 0;
     unsigned long long step_index = 0;
@@ -231,6 +232,7 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     ALLOC(e->points, np * X * 3 * 4);
     ALLOC(e->stats, MT_STATS_WORDS * 8);
 #undef ALLOC
+    e->num_sms = prop.multiProcessorCount;
     fill_params(*cfg, e->base);
     e->base.goals = e->goals;
     e->base.alive = e->alive;
@@ -493,7 +495,7 @@ static int check_ptr(const void *p, const char *name, bool required) {
     return MT_OK;
 }
 
-// launch the fused step kernel over tiles [t0, t1)
+// launch the fused step kernel over tiles [t0, t1): a persistent grid sized to the SMs
 static int launch_step(mt_env *e, const float *actions, float *obs, float *reward, uint8_t *done, float *joints,
                        bool rnd, long long t0, long long t1, cudaStream_t st) {
     StepParams P = e->base;
@@ -510,10 +512,15 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     P.tile_end = t1;
     StepFn fn = pick_kernel(e->arm, e->cfg.n_obj, rnd, obs != nullptr);
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
-    const size_t smem = (size_t)kWarpsPerBlock * P.tile_bytes + kWarpsPerBlock * sizeof(uint64_t);
+    const size_t smem = (size_t)2 * kWarpsPerBlock * P.tile_bytes + 2 * kWarpsPerBlock * sizeof(uint64_t);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kWarpsPerBlock * kTile, smem));
+    if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
     const long long tiles = t1 - t0;
-    const unsigned grid = (unsigned)((tiles + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const long long want = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long cap = (long long)per_sm * e->num_sms;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
     fn<<<grid, kWarpsPerBlock * kTile, smem, st>>>(P);
     CU(cudaGetLastError());
     e->launches++;

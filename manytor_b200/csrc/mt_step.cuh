@@ -372,152 +372,229 @@ __device__ __forceinline__ void draw_actions(const StepParams &P, long long gid,
 //   X    objectives per env, 0 = run-time P.n_obj
 //   RAND draw actions in-kernel (mt_rollout_random)   WOBS write observations
 // ---------------------------------------------------------------------------
+// Per-env scalars of one tile, prefetched into registers one tile ahead.
+template <int J>
+struct TileScalars {
+    float g[J], a[J];
+    uint32_t alive;
+    float total;
+    uint32_t cnt;
+};
+
+template <int J, bool RAND>
+__device__ __forceinline__ void load_scalars(const StepParams &P, long long env, TileScalars<J> &s) {
+    if (J == 4) {
+        float4 t = *reinterpret_cast<const float4 *>(P.goals + env * 4);
+        s.g[0] = t.x; s.g[1] = t.y; s.g[2] = t.z; s.g[3] = t.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < J; ++i) s.g[i] = P.goals[env * J + i];
+    }
+    if (!RAND) {
+        if (env >= P.n) {
+#pragma unroll
+            for (int i = 0; i < J; ++i) s.a[i] = 0.f;
+        } else if (J == 4) {
+            float4 t = __ldg(reinterpret_cast<const float4 *>(P.actions + env * 4));
+            s.a[0] = t.x; s.a[1] = t.y; s.a[2] = t.z; s.a[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < J; ++i) s.a[i] = __ldg(P.actions + env * J + i);
+        }
+    }
+    s.alive = P.alive[env];
+    s.total = P.total_reward[env];
+    s.cnt = P.counters[env];
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+//   ARM  0 = reference arm closed form (J = 4); else J of the generic chain
+//   X    objectives per env, 0 = run-time P.n_obj
+//   RAND draw actions in-kernel (mt_rollout_random)   WOBS write observations
+//
+// Persistent warps: the grid is sized to the SMs (blocks/SM from the occupancy
+// API) and every warp walks its round-robin share of the 32-env tiles, so all
+// SMs finish together.  Each warp software-pipelines its
+// tiles: while it computes tile i it has tile i+1's scalars in flight to
+// registers (coalesced vector loads) and tile i+1's objectives in flight to its
+// second shared-memory buffer (TMA bulk copy + mbarrier), and tile i-1's
+// observations draining from the other buffer to HBM (TMA bulk store).
+// ---------------------------------------------------------------------------
 template <int ARM, int X, bool RAND, bool WOBS>
 __global__ void __launch_bounds__(kWarpsPerBlock *kTile)
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int J = ARM ? ARM : 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long tile = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
-    if (tile >= P.tile_end) return;
-    const long long env0 = tile * kTile, env = env0 + lane;
     const int x = X ? X : P.n_obj;
     const int rowlen = 3 * x;
-    float *tile_s = reinterpret_cast<float *>(smem + (size_t)warp * P.tile_bytes);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)kWarpsPerBlock * P.tile_bytes) + warp;
-    const bool full = env0 + kTile <= P.n;  // warp-uniform
-    const bool valid = env < P.n;
     const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
+    unsigned char *tile_base = smem + (size_t)(2 * warp) * P.tile_bytes;   // two buffers, back to back
+    auto tile_buf = [&](int bb) { return reinterpret_cast<float *>(tile_base + (size_t)bb * P.tile_bytes); };
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * kWarpsPerBlock) * P.tile_bytes) + 2 * warp;
 
-    // 1. start the objectives tile on its way: HBM -> shared by one TMA bulk copy
+    // static round-robin tile schedule: warp w of the grid takes tiles w, w + W, w + 2W, ...  Blocks
+    // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
+    // tiles (a single ticket counter was measured first: ~37k same-address atomics per launch
+    // serialise in L2 and cost more than the imbalance they remove).
+    const long long total_warps = (long long)gridDim.x * kWarpsPerBlock;
+    const long long first = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
+    auto fetch_points = [&](long long tile, int b) {   // lane 0 only
+        mbar_expect_tx(bar + b, tile_bytes);
+        bulk_load(tile_buf(b), P.points + tile * kTile * rowlen, tile_bytes, bar + b);
+    };
+
+    long long cur = first;
+    if (cur >= P.tile_end) return;
     if (lane == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         mbar_init_fence();
-        mbar_expect_tx(bar, tile_bytes);
-        bulk_load(tile_s, P.points + env0 * rowlen, tile_bytes, bar);
+        fetch_points(cur, 0);
     }
     __syncwarp();
+    TileScalars<J> sc;
+    load_scalars<J, RAND>(P, cur * kTile + lane, sc);
+    long long nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
+    int b = 0;
+    uint32_t phase0 = 0, phase1 = 0;
 
-    // 2. per-env state and action: coalesced (vector) loads
-    float g[J], a[J];
-    if (J == 4) {
-        float4 t = *reinterpret_cast<const float4 *>(P.goals + env * 4);
-        g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < J; ++i) g[i] = P.goals[env * J + i];
-    }
-    if (RAND) {
-        draw_actions(P, P.env_id_base + env, J, a);
-    } else if (!valid) {
-#pragma unroll
-        for (int i = 0; i < J; ++i) a[i] = 0.f;
-    } else if (J == 4) {
-        float4 t = __ldg(reinterpret_cast<const float4 *>(P.actions + env * 4));
-        a[0] = t.x; a[1] = t.y; a[2] = t.z; a[3] = t.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < J; ++i) a[i] = __ldg(P.actions + env * J + i);
-    }
-    const uint32_t alive0 = P.alive[env];
-    float total = P.total_reward[env];
-    uint32_t cnt = P.counters[env];
+    while (true) {
+        const long long env0 = cur * kTile, env = env0 + lane;
+        const bool full = env0 + kTile <= P.n;  // warp-uniform
+        const bool valid = env < P.n;
 
-    // 3. kinematics while the tile is in flight
-    Frames f;
-    float jbuf[J * 3];
-    float *jout = P.joints ? jbuf : nullptr;
-    if (ARM == 0) ref_arm(g, a, P.substeps, P.inv_div, f, jout);
-    else generic_arm<J>(P, g, a, f, jout);
-    const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
+        // 1. next tile's scalars on their way to registers
+        TileScalars<J> sn;
+        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn);
 
-    // 4. objectives: obs2 in place + catch mask
-    mbar_wait(bar, 0);
-    float *row = tile_s + lane * rowlen;
-    const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
-    uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
+        // 2. kinematics of the current tile (needs no objectives)
+        if (RAND) draw_actions(P, P.env_id_base + env, J, sc.a);
+        Frames f;
+        float jbuf[J * 3];
+        float *jout = P.joints ? jbuf : nullptr;
+        if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, jout);
+        else generic_arm<J>(P, sc.g, sc.a, f, jout);
+        const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
 
-    // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
-    float rew = (alive1 != alive0) ? 1.0f : 0.0f;
-    rew = neg ? -1.0f : rew;
-    total += rew;
-    uint32_t eplen = min((cnt & 0xffffu) + 1u, 0xffffu);
-    uint32_t gsteps = min((cnt >> 16) + (neg ? 1u : 0u), 0xffffu);
-    bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
-    bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
-    const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
-
-    // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32)
-    float gn[J];
-#pragma unroll
-    for (int i = 0; i < J; ++i) gn[i] = a[i];                          // goals <- action (manytor.py:184)
-    if ((P.flags & kAutoReset) && done && valid) {
-        atomicAdd(P.stats + 1, 1ull);
-        atomicAdd(P.stats + 2, term ? 1ull : 0ull);
-        atomicAdd(P.stats + 3, (unsigned long long)(long long)total);
-        atomicAdd(P.stats + 4, (unsigned long long)eplen);
-        atomicAdd(P.stats + 5, (unsigned long long)(x - __popc(alive1)));
-        atomicAdd(P.stats + 6, (unsigned long long)gsteps);
-        const uint32_t ep = P.episode[env];                            // resets so far
-        P.episode[env] = ep + 1u;
-        float *grow = P.points + env * rowlen;
-        Frames f0;
-        f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
-        f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
-        for (int pt = 0; pt < x; ++pt) {
-            float px, py, pz;
-            if (P.obj_stream) {
-                const float *src = P.obj_stream + (((long long)(ep % (uint32_t)P.obj_sets) * P.n + env) * x + pt) * 3;
-                px = src[0]; py = src[1]; pz = src[2];
-            } else {
-                sample_point(P, P.env_id_base + env, ep, pt, px, py, pz);
-            }
-            grow[pt * 3 + 0] = px; grow[pt * 3 + 1] = py; grow[pt * 3 + 2] = pz;
-            if (WOBS && (P.flags & kObsAfterReset)) {
-                one_objective<true>(px, py, pz, f0, P.catch_tol, true);
-                row[pt * 3 + 0] = px; row[pt * 3 + 1] = py; row[pt * 3 + 2] = pz;
-            }
+        // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous
+        //    contents, tile i-1's observations, have long been read out by their bulk store)
+        if (nxt >= 0 && lane == 0) {
+            if (WOBS) bulk_wait_read0();
+            fetch_points(nxt, b ^ 1);
         }
-#pragma unroll
-        for (int i = 0; i < J; ++i) gn[i] = 0.f;
-        alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
-        total = 0.f;
-        eplen = 0u;
-        gsteps = 0u;
-    }
 
-    // 7. write back: state (coalesced), then the observation tile by one bulk store
-    if (J == 4) {
-        *reinterpret_cast<float4 *>(P.goals + env * 4) = make_float4(gn[0], gn[1], gn[2], gn[3]);
-    } else {
+        // 4. objectives of the current tile: obs2 in place + catch mask
+        mbar_wait(bar + b, b ? phase1 : phase0);
+        if (b) phase1 ^= 1u; else phase0 ^= 1u;
+        float *row = tile_buf(b) + lane * rowlen;
+        const uint32_t alive0 = sc.alive;
+        const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
+        uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
+
+        // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
+        float rew = (alive1 != alive0) ? 1.0f : 0.0f;
+        rew = neg ? -1.0f : rew;
+        float total = sc.total + rew;
+        uint32_t eplen = min((sc.cnt & 0xffffu) + 1u, 0xffffu);
+        uint32_t gsteps = min((sc.cnt >> 16) + (neg ? 1u : 0u), 0xffffu);
+        bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
+        bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
+        const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
+
+        // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32).
+        //    Rare (one env-step in ~550 for random actions), so the warp handles its ending envs
+        //    one at a time and COOPERATIVELY: lane p draws objective p (x <= 32 lanes busy) instead
+        //    of the one ending lane drawing all x while 31 lanes idle.
+        float gn[J];
 #pragma unroll
-        for (int i = 0; i < J; ++i) P.goals[env * J + i] = gn[i];
-    }
-    P.alive[env] = alive1;
-    P.total_reward[env] = total;
-    P.counters[env] = eplen | (gsteps << 16);
-    if (valid) {
-        P.reward[env] = rew;
-        P.done[env] = done;
-        if (P.joints) {
+        for (int i = 0; i < J; ++i) gn[i] = sc.a[i];                      // goals <- action (manytor.py:184)
+        const bool ending = ((P.flags & kAutoReset) != 0) & (done != 0) & valid;
+        uint32_t pending = __ballot_sync(0xffffffffu, ending);
+        if (ending) {
+            atomicAdd(P.stats + 1, 1ull);
+            atomicAdd(P.stats + 2, term ? 1ull : 0ull);
+            atomicAdd(P.stats + 3, (unsigned long long)(long long)total);
+            atomicAdd(P.stats + 4, (unsigned long long)eplen);
+            atomicAdd(P.stats + 5, (unsigned long long)(x - __popc(alive1)));
+            atomicAdd(P.stats + 6, (unsigned long long)gsteps);
 #pragma unroll
-            for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
+            for (int i = 0; i < J; ++i) gn[i] = 0.f;
+            alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
+            total = 0.f;
+            eplen = 0u;
+            gsteps = 0u;
         }
-    }
-    if (WOBS) {
-        if (full) {
-            fence_async_smem();
+        while (pending) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1u;
+            const long long renv = env0 + src;
+            const uint32_t ep = P.episode[renv];                           // resets so far (broadcast load)
             __syncwarp();
-            if (lane == 0) {
-                bulk_store(P.obs + env0 * rowlen, tile_s, tile_bytes);
-                bulk_commit();
-                bulk_wait_read0();
+            if (lane == src) P.episode[renv] = ep + 1u;
+            if (lane < x) {
+                float px, py, pz;
+                if (P.obj_stream) {
+                    const float *srcp = P.obj_stream + (((long long)(ep % (uint32_t)P.obj_sets) * P.n + renv) * x + lane) * 3;
+                    px = srcp[0]; py = srcp[1]; pz = srcp[2];
+                } else {
+                    sample_point(P, P.env_id_base + renv, ep, lane, px, py, pz);
+                }
+                float *grow = P.points + renv * rowlen + lane * 3;
+                grow[0] = px; grow[1] = py; grow[2] = pz;
+                if (WOBS && (P.flags & kObsAfterReset)) {
+                    Frames f0;
+                    f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
+                    f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
+                    one_objective<true>(px, py, pz, f0, P.catch_tol, true);
+                    float *orow = tile_buf(b) + src * rowlen + lane * 3;
+                    orow[0] = px; orow[1] = py; orow[2] = pz;
+                }
             }
-        } else if (valid) {
-            float *dst = P.obs + env * rowlen;
-            for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
         }
+        __syncwarp();
+
+        // 7. write back: state (coalesced), then the observation tile by one bulk store
+        if (J == 4) {
+            *reinterpret_cast<float4 *>(P.goals + env * 4) = make_float4(gn[0], gn[1], gn[2], gn[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < J; ++i) P.goals[env * J + i] = gn[i];
+        }
+        P.alive[env] = alive1;
+        P.total_reward[env] = total;
+        P.counters[env] = eplen | (gsteps << 16);
+        if (valid) {
+            P.reward[env] = rew;
+            P.done[env] = done;
+            if (P.joints) {
+#pragma unroll
+                for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
+            }
+        }
+        if (WOBS) {
+            if (full) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    bulk_store(P.obs + env0 * rowlen, tile_buf(b), tile_bytes);
+                    bulk_commit();
+                }
+            } else if (valid) {
+                float *dst = P.obs + env * rowlen;
+                for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
+            }
+        }
+
+        if (nxt < 0) break;
+        cur = nxt;
+        nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
+        sc = sn;
+        b ^= 1;
+        __syncwarp();
     }
+    if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
 }
 
 }  // namespace mt
