@@ -91,18 +91,23 @@ SIGNATURES = {
 }
 
 _lib = None
+_by_path = {}
 
 
 def library_path() -> str:
     return _build.LIB_PATH
 
 
-def load() -> C.CDLL:
-    """dlopen the in-tree library and bind every declared symbol (fails loudly)."""
+def load(path: str = None) -> C.CDLL:
+    """dlopen the in-tree library and bind every declared symbol (fails loudly).
+    `path` loads another build of the same ABI (A/B timing of kernel variants, tools/ab.py)."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    path = library_path()
+    if path is not None and path in _by_path:
+        return _by_path[path]
+    explicit = path is not None
+    path = path or library_path()
     if not os.path.exists(path):
         raise MantorLibraryError(
             f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -114,7 +119,10 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.mt_abi_version() != MT_ABI_VERSION:
         raise MantorLibraryError(f"ABI mismatch: library {lib.mt_abi_version()} != binding {MT_ABI_VERSION}")
-    _lib = lib
+    if explicit:
+        _by_path[path] = lib
+    else:
+        _lib = lib
     return lib
 
 

@@ -125,8 +125,9 @@ class BatchedEnvs:
     def __init__(self, n_envs: int, obj_number: int = 10, arm: ArmSpec = REFERENCE_ARM, device=None,
                  env_id_base: int = 0, horizon: int = 0, auto_reset: bool = False,
                  terminate_on_ground: bool = False, obs_after_reset: bool = False, seed: int = 0,
-                 fk_mode: int = 0, substeps: int = 25, action_low: int = -180, action_high: int = 180):
-        self._lib = _lib.load()
+                 fk_mode: int = 0, substeps: int = 25, action_low: int = -180, action_high: int = 180,
+                 lib_path: Optional[str] = None):
+        self._lib = _lib.load(lib_path)
         self._h = C.c_void_p()
         dev = _device_index(device)
         self.device = torch.device("cuda", dev)

@@ -88,6 +88,9 @@ static bool is_reference_arm(const mt_config &c) {
     return c.obs_frame == 3 && c.ground_frame_a == 3 && c.ground_frame_b == 4 && c.catch_frame == 4;
 }
 
+// X values with a specialised (compile-time, packed pair layout) kernel -- keep in sync with pick_kernel
+static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6) && (x == 10 || x == 20); }
+
 static double snap(double v) { return std::fabs(v) < 1e-12 ? 0.0 : (std::fabs(std::fabs(v) - 1.0) < 1e-12 ? (v > 0 ? 1.0 : -1.0) : v); }
 
 extern "C" int mt_abi_version(void) { return MT_ABI_VERSION; }
@@ -244,6 +247,7 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.n = e->n;
     e->base.tile_begin = 0;
     e->base.tile_end = e->n_tiles;
+    e->base.pair_layout = has_specialised_x(e->arm, cfg->n_obj) ? 1 : 0;
     *out = e;
     return MT_OK;
 }
@@ -297,7 +301,9 @@ __global__ void reset_kernel(const __grid_constant__ StepParams P, const uint8_t
         } else {
             sample_point(P, P.env_id_base + env, ep, pt, px, py, pz);
         }
-        row[pt * 3 + 0] = px; row[pt * 3 + 1] = py; row[pt * 3 + 2] = pz;
+        row[point_index(P.pair_layout, pt, 0)] = px;
+        row[point_index(P.pair_layout, pt, 1)] = py;
+        row[point_index(P.pair_layout, pt, 2)] = pz;
     }
     for (int i = 0; i < J; ++i) P.goals[env * J + i] = 0.f;           // manytor.py:220
     P.total_reward[env] = 0.f;                                        // manytor.py:221
@@ -317,7 +323,8 @@ __global__ void observe_kernel(const __grid_constant__ StepParams P, int arm, fl
     const float *row = P.points + env * 3 * x;
     float *dst = obs + env * 3 * x;
     for (int pt = 0; pt < x; ++pt) {
-        float px = row[pt * 3], py = row[pt * 3 + 1], pz = row[pt * 3 + 2];
+        float px = row[point_index(P.pair_layout, pt, 0)], py = row[point_index(P.pair_layout, pt, 1)],
+              pz = row[point_index(P.pair_layout, pt, 2)];
         one_objective<true>(px, py, pz, f, P.catch_tol, (alive >> pt) & 1u);
         dst[pt * 3] = px; dst[pt * 3 + 1] = py; dst[pt * 3 + 2] = pz;
     }
@@ -338,8 +345,10 @@ __global__ void set_points_kernel(const __grid_constant__ StepParams P, const fl
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long row = 3LL * P.n_obj;
     if (i >= P.n * row) return;
-    if (mask && !mask[i / row]) return;
-    P.points[i] = src[i];
+    const long long env = i / row;
+    if (mask && !mask[env]) return;
+    const int k = (int)(i - env * row);                               // public row-major [X][3]
+    P.points[env * row + point_index(P.pair_layout, k / 3, k % 3)] = src[i];
 }
 
 __global__ void get_points_kernel(const __grid_constant__ StepParams P, float *dst, int zero_dead) {
@@ -347,9 +356,9 @@ __global__ void get_points_kernel(const __grid_constant__ StepParams P, float *d
     const long long row = 3LL * P.n_obj;
     if (i >= P.n * row) return;
     const long long env = i / row;
-    const int pt = (int)((i - env * row) / 3);
+    const int k = (int)(i - env * row), pt = k / 3;
     const bool dead = zero_dead && !((P.alive[env] >> pt) & 1u);      // manytor.py:148
-    dst[i] = dead ? 0.f : P.points[i];
+    dst[i] = dead ? 0.f : P.points[env * row + point_index(P.pair_layout, pt, k % 3)];
 }
 
 __global__ void set_state_kernel(const __grid_constant__ StepParams P, const float *goals, const uint32_t *alive,
@@ -724,9 +733,11 @@ extern "C" int mt_fetch_env(mt_env *e, int64_t index, float *goals_host, float *
     if (goals_host) CU(cudaMemcpy(goals_host, e->goals + index * J, J * 4, cudaMemcpyDeviceToHost));
     if (total_reward_host) CU(cudaMemcpy(total_reward_host, e->total_reward + index, 4, cudaMemcpyDeviceToHost));
     if (points_host) {
-        CU(cudaMemcpy(points_host, e->points + index * X * 3, X * 12, cudaMemcpyDeviceToHost));
+        float raw[MT_MAX_OBJ * 3];
+        CU(cudaMemcpy(raw, e->points + index * X * 3, X * 12, cudaMemcpyDeviceToHost));
         for (size_t p = 0; p < X; ++p)
-            if (!((alive >> p) & 1u)) points_host[p * 3] = points_host[p * 3 + 1] = points_host[p * 3 + 2] = 0.f;  // manytor.py:148
+            for (int c = 0; c < 3; ++c)                                 // dead objectives read as zeros, manytor.py:148
+                points_host[p * 3 + c] = ((alive >> p) & 1u) ? raw[point_index(e->base.pair_layout != 0, (int)p, c)] : 0.f;
     }
     if (joints_host) {
         float *tmp = nullptr;

@@ -71,6 +71,71 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+// ------------------------------------------------------------ packed fp32x2
+// sm_100 issues two fp32 FMAs per lane from one instruction (SASS FFMA2 / FADD2 /
+// FMUL2 on an aligned register pair, with free -x / |x| and scalar-broadcast
+// operands).  The kernel is bound by instruction issue, not by the FMA pipe, so
+// independent pairs of evaluations (two objectives, two joints, sin+cos of one
+// angle, two cosine sequences) are packed: same flops, half the issue slots.
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// polynomial cores shared by the scalar and packed sin/cos: sin(pi r)/r and cos(pi r) in u = r^2
+__device__ __forceinline__ float2 sinpi_poly2(float2 r, float2 u) {
+    return mul2(fma2(fma2(fma2(bc2(-0.58907866f), u, bc2(2.5497673f)), u, bc2(-5.1677079f)), u, bc2(3.14159274f)), r);
+}
+__device__ __forceinline__ float2 cospi_poly2(float2 u) {
+    return fma2(fma2(fma2(fma2(bc2(0.23132971f), u, bc2(-1.33504462f)), u, bc2(4.05870724f)), u, bc2(-4.93480206f)), u, bc2(1.0f));
+}
+
+__device__ __forceinline__ void quadrant_fix(int q, float sp, float cp, float &s, float &c) {
+    float ss = (q & 1) ? cp : sp;
+    float cc = (q & 1) ? sp : cp;
+    s = __int_as_float(__float_as_int(ss) ^ ((q & 2) << 30));
+    c = __int_as_float(__float_as_int(cc) ^ (((q + 1) & 2) << 30));
+}
+
+// sin/cos of TWO angles in degrees at once (same reduction as sincos_deg; the round-to-integer
+// is done with the 1.5*2^23 magic constant so it packs too; valid for |x| < 3e8 degrees).
+__device__ __forceinline__ void sincos_deg2(float2 x, float2 &s, float2 &c) {
+    const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f, magic = 12582912.0f;
+    float2 t = fma2(x, bc2(inv_lo), mul2(x, bc2(inv_hi)));
+    float2 m = fma2(t, bc2(2.0f), bc2(magic));      // low mantissa bits of m = rint(2t)
+    float2 n = add2(m, bc2(-magic));
+    float2 r = fma2(n, bc2(-0.5f), t);
+    float2 u = mul2(r, r);
+    float2 sp = sinpi_poly2(r, u), cp = cospi_poly2(u);
+    quadrant_fix(__float_as_int(m.x), sp.x, cp.x, s.x, c.x);
+    quadrant_fix(__float_as_int(m.y), sp.y, cp.y, s.y, c.y);
+}
+
+// two SMALL angles (|x| <= 45 degrees): quadrant 0, no fix-up
+__device__ __forceinline__ void sincos_deg_small2(float2 x, float2 &s, float2 &c) {
+    const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f;
+    float2 r = fma2(x, bc2(inv_lo), mul2(x, bc2(inv_hi)));
+    float2 u = mul2(r, r);
+    s = sinpi_poly2(r, u);
+    c = cospi_poly2(u);
+}
+
+// 2 atan(t) in degrees for two arguments in [0, 1] (the half-angle form of atan2_deg_pos)
+__device__ __forceinline__ float2 atan_half_deg2(float2 t) {
+    float2 s = mul2(t, t);
+    float2 p = bc2(-0.54776114f);
+    p = fma2(p, s, bc2(2.81390548f));
+    p = fma2(p, s, bc2(-6.86439371f));
+    p = fma2(p, s, bc2(11.3934412f));
+    p = fma2(p, s, bc2(-16.0764885f));
+    p = fma2(p, s, bc2(22.8855038f));
+    p = fma2(p, s, bc2(-38.1957664f));
+    p = fma2(p, s, bc2(114.591545f));
+    return mul2(p, t);
+}
+
 // ------------------------------------------------------------------ Philox
 // Philox4x32-10 (Salmon et al., SC'11), the counter-based generator: no
 // per-env RNG state is kept in HBM; streams are keyed by (seed, env id, index).

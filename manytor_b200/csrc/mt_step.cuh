@@ -67,6 +67,7 @@ struct StepParams {
     float zero_anchor[3];
     JointConst arm[MT_MAX_JOINTS];
     uint32_t tile_bytes;
+    int32_t pair_layout;     // objectives stored pair-interleaved (see point_index)
 };
 
 // ---------------------------------------------------------------------------
@@ -103,29 +104,29 @@ __device__ __forceinline__ void rot_back(float &c, float &s, float cd, float sd)
 // count), run backwards from the exact final pose: 13 instructions per sub-pose
 // instead of 3 plane rotations + products.  tools/emulate_subpose.py compares it
 // with fp64: max |dz| 3.5e-5 over 4e5 random steps, no ground-flag flips.
-struct CosSeq {
-    float x, d, na;  // value, backward difference, -4 sin^2(delta/2)
-    // amp * cos(theta - k * delta), k = 0, 1, ...; (sh, ch) = sin/cos(delta / 2)
-    __device__ __forceinline__ void init(float amp, float cth, float sth, float sh, float ch) {
-        float t = sh + sh;
-        na = -(t * t);                    // -4 sh^2
-        x = amp * cth;
+// Two cosine sequences advanced together (one FADD2 + one FFMA2 per sub-pose).
+struct CosSeq2 {
+    float2 x, d, na;  // values, backward differences, -4 sin^2(delta/2)
+    // amp * cos(theta - k * delta), k = 0, 1, ...; (sh, ch) = sin/cos(delta / 2), per half
+    __device__ __forceinline__ void init(float2 amp, float2 cth, float2 sth, float2 sh, float2 ch) {
+        float2 t = add2(sh, sh);
+        na = neg2(mul2(t, t));            // -4 sh^2
+        x = mul2(amp, cth);
         // amp (cos(theta - delta) - cos theta) = amp sin(theta) sin(delta) - 2 sh^2 x
-        d = fmaf(amp * sth, t * ch, 0.5f * na * x);
+        d = fma2(mul2(amp, sth), mul2(t, ch), mul2(mul2(bc2(0.5f), na), x));
     }
     __device__ __forceinline__ void back() {
-        x += d;
-        d = fmaf(na, x, d);
+        x = add2(x, d);
+        d = fma2(na, x, d);
     }
 };
 
 __device__ __forceinline__ void ref_arm(const float *g, const float *a, int substeps, float inv_div, Frames &f,
                                         float *jout /* 12 floats or nullptr */) {
-    float s0, c0, s1, c1, s2, c2, s3, c3;
-    sincos_deg(a[0], s0, c0);
-    sincos_deg(a[1], s1, c1);
-    sincos_deg(a[2], s2, c2);
-    sincos_deg(a[3], s3, c3);
+    float2 s01, c01, s23, c23;
+    sincos_deg2(make_float2(a[0], a[1]), s01, c01);
+    sincos_deg2(make_float2(a[2], a[3]), s23, c23);
+    const float s0 = s01.x, c0 = c01.x, s1 = s01.y, c1 = c01.y, s2 = s23.x, c2 = c23.x, s3 = s23.y, c3 = c23.y;
     const float L1 = 24.3f, L2 = 27.0f, H = 4.3f;
     float ez = fmaf(L1, c1, H);
     float k = L1 * s1;
@@ -150,34 +151,36 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
         // half steps in degrees; the small-angle sin/cos holds for |half step| <= 45, i.e. any
         // target within +-2160 degrees of the current pose at 25 sub-poses (else: general path)
         const float hs = 0.5f * inv_div;
-        const float h1 = (a[1] - g[1]) * hs, h2 = (a[2] - g[2]) * hs, h3 = (a[3] - g[3]) * hs;
-        float sh1, ch1, sh2, ch2, sh3, ch3;
-        const bool small = fmaxf(fmaxf(fabsf(h1), fabsf(h2)), fabsf(h3)) <= 45.0f;
+        const float2 h12 = make_float2((a[1] - g[1]) * hs, (a[2] - g[2]) * hs);
+        const float2 h33 = bc2((a[3] - g[3]) * hs);
+        float2 sh12, ch12, sh33, ch33;
+        const bool small = fmaxf(fmaxf(fabsf(h12.x), fabsf(h12.y)), fabsf(h33.x)) <= 45.0f;
         if (__all_sync(__activemask(), small)) {
-            sincos_deg_small(h1, sh1, ch1);
-            sincos_deg_small(h2, sh2, ch2);
-            sincos_deg_small(h3, sh3, ch3);
+            sincos_deg_small2(h12, sh12, ch12);
+            sincos_deg_small2(h33, sh33, ch33);
         } else {
-            sincos_deg(h1, sh1, ch1);
-            sincos_deg(h2, sh2, ch2);
-            sincos_deg(h3, sh3, ch3);
+            sincos_deg2(h12, sh12, ch12);
+            sincos_deg2(h33, sh33, ch33);
         }
-        // A = th1 + th3, B = th1 - th3 and their half steps by angle addition
-        const float cA = fmaf(c1, c3, -(s1 * s3)), sA = fmaf(s1, c3, c1 * s3);
-        const float cB = fmaf(c1, c3, s1 * s3), sB = fmaf(s1, c3, -(c1 * s3));
-        const float chA = fmaf(ch1, ch3, -(sh1 * sh3)), shA = fmaf(sh1, ch3, ch1 * sh3);
-        const float chB = fmaf(ch1, ch3, sh1 * sh3), shB = fmaf(sh1, ch3, -(ch1 * sh3));
-        CosSeq q1, q2, qA, qB;
-        q1.init(L1, c1, s1, sh1, ch1);
-        q2.init(1.0f, c2, s2, sh2, ch2);
-        qA.init(0.5f * L2, cA, sA, shA, chA);
-        qB.init(0.5f * L2, cB, sB, shB, chB);
+        // A = th1 + th3, B = th1 - th3 and their half steps by angle addition, A in .x, B in .y:
+        // cos(th1 +- th3) = c1 c3 -+ s1 s3, sin(th1 +- th3) = s1 c3 +- c1 s3
+        const float2 pm = make_float2(1.0f, -1.0f);
+        const float2 cAB = fma2(bc2(-(s1 * s3)), pm, bc2(c1 * c3));
+        const float2 sAB = fma2(bc2(c1 * s3), pm, bc2(s1 * c3));
+        const float sh1 = sh12.x, ch1 = ch12.x, sh3 = sh33.x, ch3 = ch33.x;
+        const float2 chAB = fma2(bc2(-(sh1 * sh3)), pm, bc2(ch1 * ch3));
+        const float2 shAB = fma2(bc2(ch1 * sh3), pm, bc2(sh1 * ch3));
+        CosSeq2 q12, qAB;
+        q12.init(make_float2(L1, 1.0f), make_float2(c1, c2), make_float2(s1, s2), sh12, ch12);
+        qAB.init(bc2(0.5f * L2), cAB, sAB, shAB, chAB);
         float m = 3.0e38f;
 #pragma unroll 4
         for (int p = 1; p < substeps; ++p) {
-            q1.back(); q2.back(); qA.back(); qB.back();
-            float t = fmaf(q2.x, qA.x - qB.x, q1.x + (qA.x + qB.x));
-            m = fminf(m, fminf(q1.x, t));
+            q12.back();
+            qAB.back();
+            const float2 sd = fma2(bc2(qAB.x.y), pm, bc2(qAB.x.x));     // (uA + uB, uA - uB)
+            const float t = fmaf(q12.x.y, sd.y, q12.x.x + sd.x);
+            m = fminf(m, fminf(q12.x.x, t));
         }
         zmin = fminf(zmin, m + H);
     }
@@ -275,9 +278,22 @@ __device__ __forceinline__ bool one_objective(float &px, float &py, float &pz, c
     return caught;
 }
 
-// Vector width for the in-place row walk: the widest power of two (<= 4 floats)
-// dividing the row length 3X, which makes the per-lane row stride odd in
-// vector units and the shared-memory accesses bank-conflict free.
+// Layout of one env's objectives inside its row of 3X floats.
+//   pair layout (X even, the specialised kernels): objectives are stored two by two,
+//   component-interleaved -- [x0 x1 | y0 y1 | z0 z1] per pair -- so one 64-bit shared-memory load
+//   yields the packed operand (x0, x1) for the FADD2/FFMA2 pipeline; observations are written back
+//   in place in the public row-major order [d0 r0 t0 d1 r1 t1], which spans the same 6 floats.
+//   plain layout (run-time X): row-major [x y z] per objective.
+// Either way a lane only ever touches its own row, and the row stride (3X words) keeps 64/128-bit
+// accesses of consecutive lanes on distinct banks for X = 10 / 20.
+template <int X> struct PairLayout { static constexpr bool value = (X != 0) && (X % 2 == 0); };
+
+__host__ __device__ __forceinline__ int point_index(bool pair_layout, int pt, int comp) {
+    return pair_layout ? (pt >> 1) * 6 + comp * 2 + (pt & 1) : pt * 3 + comp;
+}
+
+// Vector width for the plain in-place row walk: the widest power of two (<= 4 floats) dividing
+// the row length 3X, which keeps the per-lane row stride odd in vector units (no bank conflicts).
 template <int X> struct RowVec { static constexpr int value = (X % 4 == 0) ? 4 : ((X % 2 == 0) ? 2 : 1); };
 template <> struct RowVec<0> { static constexpr int value = 1; };
 
@@ -304,28 +320,73 @@ __device__ __forceinline__ void vstore(float *p, const float *v) {
     *reinterpret_cast<T *>(p) = t;
 }
 
-// Walk one env's row of objectives in shared memory: V objectives (3 vectors
-// of V floats) per iteration, observations written back in place.  Returns
-// the bitmask of objectives inside the catch cube.
+// Two objectives at once, packed (manytor.py:141-153, 17-22, 158-168).  In: (x0,x1), (y0,y1),
+// (z0,z1).  Out: o[6] = d0 r0 t0 d1 r1 t1; returns the two catch bits.
+template <bool WOBS>
+__device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 PZ, const Frames &f, float tol,
+                                                   bool alive0, bool alive1, float *o) {
+    const float2 cx = add2(PX, bc2(-f.catcher[0])), cy = add2(PY, bc2(-f.catcher[1])), cz = add2(PZ, bc2(-f.catcher[2]));
+    const bool c0 = (fabsf(cx.x) <= tol) & (fabsf(cy.x) <= tol) & (fabsf(cz.x) <= tol);
+    const bool c1 = (fabsf(cx.y) <= tol) & (fabsf(cy.y) <= tol) & (fabsf(cz.y) <= tol);
+    if (WOBS) {
+        const float2 dx = add2(PX, bc2(-f.anchor[0])), dy = add2(PY, bc2(-f.anchor[1])), dz = add2(PZ, bc2(-f.anchor[2]));
+        const float2 h2 = fma2(dx, dx, mul2(dy, dy));
+        const float2 d2 = fma2(dz, dz, h2);
+        const float2 h = make_float2(fast_sqrt(h2.x), fast_sqrt(h2.y));
+        const float2 dist = make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y));
+        // atan2(|dx|, |dy|) = 2 atan(|dx| / (|dy| + h)); atan2(h, |dz|) = 2 atan(h / (|dz| + dist)).
+        // The +1e-30 keeps 0/0 -> 0 like math.atan2(0, 0) and is absorbed by any other denominator.
+        const float2 dr = add2(add2(abs2(dy), h), bc2(1e-30f));
+        const float2 dt = add2(add2(abs2(dz), dist), bc2(1e-30f));
+        const float2 tr = mul2(abs2(dx), make_float2(fast_rcp(dr.x), fast_rcp(dr.y)));
+        const float2 tt = mul2(h, make_float2(fast_rcp(dt.x), fast_rcp(dt.y)));
+        const float2 R = atan_half_deg2(tr), T = atan_half_deg2(tt);
+        o[0] = alive0 ? dist.x : 0.0f; o[1] = alive0 ? R.x : 0.0f; o[2] = alive0 ? T.x : 0.0f;
+        o[3] = alive1 ? dist.y : 0.0f; o[4] = alive1 ? R.y : 0.0f; o[5] = alive1 ? T.y : 0.0f;
+    }
+    return (c0 ? 1u : 0u) | (c1 ? 2u : 0u);
+}
+
+// Walk one env's row of objectives in shared memory, observations written back in place.
+// Returns the bitmask of objectives inside the catch cube.
 template <int X, bool WOBS>
 __device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f, float tol, uint32_t alive) {
-    constexpr int V = RowVec<X>::value;
     uint32_t caught = 0;
-    const int iters = (X ? X : x) / V;
+    if (PairLayout<X>::value) {
 #pragma unroll
-    for (int it = 0; it < iters; ++it) {
-        float v[3 * V];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) vload<V>(row + (it * 3 + i) * V, v + i * V);
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const int pt = it * V + j;
-            bool c = one_objective<WOBS>(v[3 * j], v[3 * j + 1], v[3 * j + 2], f, tol, (alive >> pt) & 1u);
-            caught |= c ? (1u << pt) : 0u;
+        for (int pr = 0; pr < X / 2; ++pr) {
+            float *q = row + pr * 6;
+            const float2 PX = *reinterpret_cast<const float2 *>(q);
+            const float2 PY = *reinterpret_cast<const float2 *>(q + 2);
+            const float2 PZ = *reinterpret_cast<const float2 *>(q + 4);
+            float o[6];
+            const uint32_t c = pair_objective<WOBS>(PX, PY, PZ, f, tol, (alive >> (2 * pr)) & 1u,
+                                                    (alive >> (2 * pr + 1)) & 1u, o);
+            caught |= c << (2 * pr);
+            if (WOBS) {
+                *reinterpret_cast<float2 *>(q) = make_float2(o[0], o[1]);
+                *reinterpret_cast<float2 *>(q + 2) = make_float2(o[2], o[3]);
+                *reinterpret_cast<float2 *>(q + 4) = make_float2(o[4], o[5]);
+            }
         }
-        if (WOBS) {
+    } else {
+        constexpr int V = RowVec<X>::value;
+        const int iters = (X ? X : x) / V;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) vstore<V>(row + (it * 3 + i) * V, v + i * V);
+        for (int it = 0; it < iters; ++it) {
+            float v[3 * V];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) vload<V>(row + (it * 3 + i) * V, v + i * V);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const int pt = it * V + j;
+                bool c = one_objective<WOBS>(v[3 * j], v[3 * j + 1], v[3 * j + 2], f, tol, (alive >> pt) & 1u);
+                caught |= c ? (1u << pt) : 0u;
+            }
+            if (WOBS) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) vstore<V>(row + (it * 3 + i) * V, v + i * V);
+            }
         }
     }
     return caught;
@@ -366,12 +427,6 @@ __device__ __forceinline__ void draw_actions(const StepParams &P, long long gid,
     }
 }
 
-// ---------------------------------------------------------------------------
-// the kernel
-//   ARM  0 = reference arm closed form (J = 4); else J of the generic chain
-//   X    objectives per env, 0 = run-time P.n_obj
-//   RAND draw actions in-kernel (mt_rollout_random)   WOBS write observations
-// ---------------------------------------------------------------------------
 // Per-env scalars of one tile, prefetched into registers one tile ahead.
 template <int J>
 struct TileScalars {
@@ -382,29 +437,30 @@ struct TileScalars {
 };
 
 template <int J, bool RAND>
-__device__ __forceinline__ void load_scalars(const StepParams &P, long long env, TileScalars<J> &s) {
+__device__ __forceinline__ void load_scalars(const StepParams &P, long long env, TileScalars<J> &s, uint64_t keep,
+                                             uint64_t stream) {
     if (J == 4) {
-        float4 t = *reinterpret_cast<const float4 *>(P.goals + env * 4);
+        float4 t = ld_hint(reinterpret_cast<const float4 *>(P.goals + env * 4), keep);
         s.g[0] = t.x; s.g[1] = t.y; s.g[2] = t.z; s.g[3] = t.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < J; ++i) s.g[i] = P.goals[env * J + i];
+        for (int i = 0; i < J; ++i) s.g[i] = ld_hint(P.goals + env * J + i, keep);
     }
     if (!RAND) {
         if (env >= P.n) {
 #pragma unroll
             for (int i = 0; i < J; ++i) s.a[i] = 0.f;
         } else if (J == 4) {
-            float4 t = __ldg(reinterpret_cast<const float4 *>(P.actions + env * 4));
+            float4 t = ld_hint(reinterpret_cast<const float4 *>(P.actions + env * 4), stream);
             s.a[0] = t.x; s.a[1] = t.y; s.a[2] = t.z; s.a[3] = t.w;
         } else {
 #pragma unroll
-            for (int i = 0; i < J; ++i) s.a[i] = __ldg(P.actions + env * J + i);
+            for (int i = 0; i < J; ++i) s.a[i] = ld_hint(P.actions + env * J + i, stream);
         }
     }
-    s.alive = P.alive[env];
-    s.total = P.total_reward[env];
-    s.cnt = P.counters[env];
+    s.alive = ld_hint(P.alive + env, keep);
+    s.total = ld_hint(P.total_reward + env, keep);
+    s.cnt = ld_hint(P.counters + env, keep);
 }
 
 // ---------------------------------------------------------------------------
@@ -438,11 +494,12 @@ step_kernel(const __grid_constant__ StepParams P) {
     // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
     // tiles (a single ticket counter was measured first: ~37k same-address atomics per launch
     // serialise in L2 and cost more than the imbalance they remove).
+    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     const long long total_warps = (long long)gridDim.x * kWarpsPerBlock;
     const long long first = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
     auto fetch_points = [&](long long tile, int b) {   // lane 0 only
         mbar_expect_tx(bar + b, tile_bytes);
-        bulk_load(tile_buf(b), P.points + tile * kTile * rowlen, tile_bytes, bar + b);
+        bulk_load_hint(tile_buf(b), P.points + tile * kTile * rowlen, tile_bytes, bar + b, pol_stream);
     };
 
     long long cur = first;
@@ -455,7 +512,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     }
     __syncwarp();
     TileScalars<J> sc;
-    load_scalars<J, RAND>(P, cur * kTile + lane, sc);
+    load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
     long long nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
     int b = 0;
     uint32_t phase0 = 0, phase1 = 0;
@@ -467,7 +524,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 
         // 1. next tile's scalars on their way to registers
         TileScalars<J> sn;
-        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn);
+        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
         // 2. kinematics of the current tile (needs no objectives)
         if (RAND) draw_actions(P, P.env_id_base + env, J, sc.a);
@@ -541,8 +598,10 @@ step_kernel(const __grid_constant__ StepParams P) {
                 } else {
                     sample_point(P, P.env_id_base + renv, ep, lane, px, py, pz);
                 }
-                float *grow = P.points + renv * rowlen + lane * 3;
-                grow[0] = px; grow[1] = py; grow[2] = pz;
+                float *grow = P.points + renv * rowlen;
+                grow[point_index(PairLayout<X>::value, lane, 0)] = px;
+                grow[point_index(PairLayout<X>::value, lane, 1)] = py;
+                grow[point_index(PairLayout<X>::value, lane, 2)] = pz;
                 if (WOBS && (P.flags & kObsAfterReset)) {
                     Frames f0;
                     f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
@@ -557,17 +616,17 @@ step_kernel(const __grid_constant__ StepParams P) {
 
         // 7. write back: state (coalesced), then the observation tile by one bulk store
         if (J == 4) {
-            *reinterpret_cast<float4 *>(P.goals + env * 4) = make_float4(gn[0], gn[1], gn[2], gn[3]);
+            st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
         } else {
 #pragma unroll
-            for (int i = 0; i < J; ++i) P.goals[env * J + i] = gn[i];
+            for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, gn[i], pol_keep);
         }
-        P.alive[env] = alive1;
-        P.total_reward[env] = total;
-        P.counters[env] = eplen | (gsteps << 16);
+        st_hint(P.alive + env, alive1, pol_keep);
+        st_hint(P.total_reward + env, total, pol_keep);
+        st_hint(P.counters + env, eplen | (gsteps << 16), pol_keep);
         if (valid) {
-            P.reward[env] = rew;
-            P.done[env] = done;
+            st_hint(P.reward + env, rew, pol_stream);
+            st_hint(P.done + env, done, pol_stream);
             if (P.joints) {
 #pragma unroll
                 for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
@@ -578,7 +637,7 @@ step_kernel(const __grid_constant__ StepParams P) {
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_store(P.obs + env0 * rowlen, tile_buf(b), tile_bytes);
+                    bulk_store_hint(P.obs + env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
                     bulk_commit();
                 }
             } else if (valid) {
