@@ -142,14 +142,14 @@ def cpu_baseline_single_core(budget_s: float = 12.0) -> dict:
     dt = time.perf_counter() - t0
     from oracle.scalar_port import multienv_loop
     t1 = time.perf_counter()
-    es, _ = multienv_loop(16, OBJ, 12, seed=0)
+    es, _ = multienv_loop(64, OBJ, 60, seed=0)       # Multienv((8,8), 10)-sized, ~4 s
     dts = time.perf_counter() - t1
     return {"value": n * steps / dt, "unit": METRIC, "cores": 1, "kind": "port",
             "sample": f"oracle/manytor_oracle.py (vectorised fp64 numpy restatement of manytor.py:175-260), "
                       f"{n} envs x {steps} steps, x={OBJ}, random integer actions, {dt:.1f}s on 1 core",
             "scalar_loop_value": es / dts,
             "scalar_loop_sample": f"oracle/scalar_port.py (per-env Python loop shaped like test_multi.py / "
-                                  f"manytor.py:115-122), 16 envs x 12 steps in {dts:.1f}s on 1 core"}
+                                  f"manytor.py:115-122), 64 envs x 60 steps in {dts:.1f}s on 1 core"}
 
 
 def run_reference_arm(args) -> None:
