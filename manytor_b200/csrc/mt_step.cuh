@@ -230,27 +230,48 @@ __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g,
         if (jout && frame >= 2) { jout[(frame - 1) * 3 + 0] = t[0]; jout[(frame - 1) * 3 + 1] = t[1]; jout[(frame - 1) * 3 + 2] = t[2]; }
     }
     float zmin = fminf(zA, zB);
-    float cd[J], sd[J];
-#pragma unroll
-    for (int i = 1; i < J; ++i) sincos_deg((a[i] - g[i]) * P.inv_div, sd[i], cd[i]);
-    for (int p = 1; p < P.substeps; ++p) {
-        float r0 = 0.f, r1 = P.arm[0].sa, r2 = P.arm[0].ca, tz = P.arm[0].d;
-        float za = (P.ground_a <= 1) ? ((P.ground_a == 1) ? tz : 0.f) : 0.f;
-        float zb = (P.ground_b <= 1) ? ((P.ground_b == 1) ? tz : 0.f) : 0.f;
+    // Interior sub-poses k = 1 .. M (k steps back from the final pose), TWO per iteration: the .x
+    // lane of every packed value is sub-pose k, the .y lane sub-pose k+1, and both advance by
+    // 2*delta per iteration (FFMA2/FADD2: half the instructions, half the rotations' rounding).
+    // M even: pairs (1,2), (3,4), ..; M odd: (0,1), (2,3), .. (re-testing the final pose is harmless).
+    const int M = P.substeps - 1;
+    if (M > 0) {
+        const bool even = (M & 1) == 0;
+        float2 c2[J], s2[J];
+        float cdd[J], sdd[J];
 #pragma unroll
         for (int i = 1; i < J; ++i) {
-            rot_back(c[i], s[i], cd[i], sd[i]);
-            const JointConst q = P.arm[i];
-            float u = fmaf(r0, c[i], r1 * s[i]);
-            float v = fmaf(r1, c[i], -(r0 * s[i]));
-            tz = fmaf(q.a, u, fmaf(q.d, r2, tz));
-            r0 = u;
-            r1 = fmaf(v, q.ca, r2 * q.sa);
-            r2 = fmaf(r2, q.ca, -(v * q.sa));
-            if (i + 1 == P.ground_a) za = tz;
-            if (i + 1 == P.ground_b) zb = tz;
+            float sd, cd;
+            sincos_deg((a[i] - g[i]) * P.inv_div, sd, cd);
+            const float c1 = fmaf(c[i], cd, s[i] * sd), s1 = fmaf(s[i], cd, -(c[i] * sd));      // one step back
+            cdd[i] = fmaf(cd, cd, -(sd * sd));                                                   // cos / sin of 2 delta
+            sdd[i] = 2.0f * sd * cd;
+            const float cb = fmaf(c[i], cdd[i], s[i] * sdd[i]), sb = fmaf(s[i], cdd[i], -(c[i] * sdd[i]));  // two back
+            c2[i] = even ? make_float2(c1, cb) : make_float2(c[i], c1);
+            s2[i] = even ? make_float2(s1, sb) : make_float2(s[i], s1);
         }
-        zmin = fminf(zmin, fminf(za, zb));
+        const int iters = (M + 1) >> 1;
+        for (int it = 0; it < iters; ++it) {
+            float2 r0 = bc2(0.f), r1 = bc2(P.arm[0].sa), r2 = bc2(P.arm[0].ca), tz = bc2(P.arm[0].d);
+            float2 za = bc2((P.ground_a == 1) ? P.arm[0].d : 0.f), zb = bc2((P.ground_b == 1) ? P.arm[0].d : 0.f);
+#pragma unroll
+            for (int i = 1; i < J; ++i) {
+                const JointConst q = P.arm[i];
+                const float2 u = fma2(r0, c2[i], mul2(r1, s2[i]));
+                const float2 v = fma2(r1, c2[i], neg2(mul2(r0, s2[i])));
+                tz = fma2(bc2(q.a), u, fma2(bc2(q.d), r2, tz));
+                r0 = u;
+                r1 = fma2(v, bc2(q.ca), mul2(r2, bc2(q.sa)));
+                r2 = fma2(r2, bc2(q.ca), neg2(mul2(v, bc2(q.sa))));
+                if (i + 1 == P.ground_a) za = tz;
+                if (i + 1 == P.ground_b) zb = tz;
+                // advance this joint by 2 delta for the next pair
+                const float2 nc = fma2(c2[i], bc2(cdd[i]), mul2(s2[i], bc2(sdd[i])));
+                s2[i] = fma2(s2[i], bc2(cdd[i]), neg2(mul2(c2[i], bc2(sdd[i]))));
+                c2[i] = nc;
+            }
+            zmin = fminf(zmin, fminf(fminf(za.x, za.y), fminf(zb.x, zb.y)));
+        }
     }
     f.zmin = zmin;
 }
@@ -478,7 +499,7 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, long long env,
 // observations draining from the other buffer to HBM (TMA bulk store).
 // ---------------------------------------------------------------------------
 template <int ARM, int X, bool RAND, bool WOBS>
-__global__ void __launch_bounds__(kWarpsPerBlock *kTile)
+__global__ void __launch_bounds__(kWarpsPerBlock *kTile, (ARM == 0) ? 7 : 1)
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int J = ARM ? ARM : 4;

@@ -43,10 +43,14 @@ def bench(name, n, x, arm, K=300, rounds=5, **kw):
 
 
 res = {}
-res["config2: 4096 envs, J=4, x=10 (lives in L2)"] = bench("config2: 4096 envs, J=4, x=10 (in L2)", 4096, 10, REFERENCE_ARM)
-res["config3: 2^20 envs, J=4, x=10"] = bench("config3: 2^20 envs, J=4, x=10", 1 << 20, 10, REFERENCE_ARM)
-res["config3 via generic DH chain (fk_mode=1)"] = bench("config3 via generic DH chain (fk_mode=1)", 1 << 20, 10, REFERENCE_ARM, fk_mode=1)
-res["config5: 2^20 envs, J=6 UR5, x=20"] = bench("config5: 2^20 envs, J=6 UR5, x=20", 1 << 20, 20, UR5_ARM)
-res["2^22 envs, J=4, x=10"] = bench("2^22 envs, J=4, x=10", 1 << 22, 10, REFERENCE_ARM, K=100)
+CASES = [("config2: 4096 envs, J=4, x=10 (in L2)", 4096, 10, REFERENCE_ARM, {}),
+         ("config3: 2^20 envs, J=4, x=10", 1 << 20, 10, REFERENCE_ARM, {}),
+         ("config3 via generic DH chain (fk_mode=1)", 1 << 20, 10, REFERENCE_ARM, dict(fk_mode=1)),
+         ("config5: 2^20 envs, J=6 UR5, x=20", 1 << 20, 20, UR5_ARM, {}),
+         ("2^22 envs, J=4, x=10", 1 << 22, 10, REFERENCE_ARM, dict(K=100))]
+only = sys.argv[1] if len(sys.argv) > 1 else ""
+for name, n, x, arm, kw in CASES:
+    if only in name:
+        res[name] = bench(name, n, x, arm, **kw)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/bench_configs.json", "w"), indent=1)
