@@ -521,7 +521,8 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     P.tile_end = t1;
     StepFn fn = pick_kernel(e->arm, e->cfg.n_obj, rnd, obs != nullptr);
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
-    const size_t smem = (size_t)2 * kWarpsPerBlock * P.tile_bytes + 2 * kWarpsPerBlock * sizeof(uint64_t);
+    const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
+    const size_t smem = nb * kWarpsPerBlock * P.tile_bytes + nb * kWarpsPerBlock * sizeof(uint64_t);
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kWarpsPerBlock * kTile, smem));

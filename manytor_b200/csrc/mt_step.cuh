@@ -187,6 +187,51 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
     f.zmin = zmin;
 }
 
+// z of the two ground frames at two sub-poses per iteration (lanes .x/.y), minimum over `iters`
+// iterations.  The z row e_z^T A_1 .. A_k does not depend on joint 0's angle: it starts as the
+// constant (0, sin a0, cos a0 | d0) and is pushed through joints 1 .. J-1.
+template <int J, bool STD>
+__device__ __forceinline__ float subpose_zmin(const StepParams &P, float2 *c2, float2 *s2, const float *cdd,
+                                              const float *sdd, int iters, float zmin) {
+    const float sa0 = P.arm[0].sa, ca0 = P.arm[0].ca, d0 = P.arm[0].d;
+    for (int it = 0; it < iters; ++it) {
+        float2 r0, r1, r2, tz;
+        float2 za = bc2(d0), zb = bc2(d0);          // frame 1 (only reachable through run-time selectors or J = 2)
+        if (!STD) {
+            za = bc2((P.ground_a == 1) ? d0 : 0.f);
+            zb = bc2((P.ground_b == 1) ? d0 : 0.f);
+        }
+#pragma unroll
+        for (int i = 1; i < J; ++i) {
+            const JointConst q = P.arm[i];
+            float2 u, v;
+            if (i == 1) {                           // r0 = 0, r1 = sa0, r2 = ca0 are constants here
+                u = mul2(bc2(sa0), s2[1]);
+                v = mul2(bc2(sa0), c2[1]);
+                tz = fma2(bc2(q.a), u, bc2(fmaf(q.d, ca0, d0)));
+                r1 = fma2(v, bc2(q.ca), bc2(ca0 * q.sa));
+                r2 = fma2(v, bc2(-q.sa), bc2(ca0 * q.ca));
+            } else {
+                u = fma2(r0, c2[i], mul2(r1, s2[i]));
+                v = fma2(r1, c2[i], neg2(mul2(r0, s2[i])));
+                tz = fma2(bc2(q.a), u, fma2(bc2(q.d), r2, tz));
+                const float2 r2o = r2;
+                r2 = fma2(r2o, bc2(q.ca), neg2(mul2(v, bc2(q.sa))));
+                r1 = fma2(v, bc2(q.ca), mul2(r2o, bc2(q.sa)));
+            }
+            r0 = u;
+            if (STD ? (i + 1 == J - 1) : (i + 1 == P.ground_a)) za = tz;
+            if (STD ? (i + 1 == J) : (i + 1 == P.ground_b)) zb = tz;
+            // advance this joint by 2 delta for the next pair of sub-poses
+            const float2 nc = fma2(c2[i], bc2(cdd[i]), mul2(s2[i], bc2(sdd[i])));
+            s2[i] = fma2(s2[i], bc2(cdd[i]), neg2(mul2(c2[i], bc2(sdd[i]))));
+            c2[i] = nc;
+        }
+        zmin = fminf(zmin, fminf(fminf(za.x, za.y), fminf(zb.x, zb.y)));
+    }
+    return zmin;
+}
+
 // Generic J-joint DH chain (the reference's "pluggable fk", README.md:20).
 // Final pose: 3x4 affine prefix products, origins of every frame.  Sub-poses:
 // only the z row e_z^T A_1 ... A_k is propagated (10 FMA-class ops per joint);
@@ -251,27 +296,10 @@ __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g,
             s2[i] = even ? make_float2(s1, sb) : make_float2(s[i], s1);
         }
         const int iters = (M + 1) >> 1;
-        for (int it = 0; it < iters; ++it) {
-            float2 r0 = bc2(0.f), r1 = bc2(P.arm[0].sa), r2 = bc2(P.arm[0].ca), tz = bc2(P.arm[0].d);
-            float2 za = bc2((P.ground_a == 1) ? P.arm[0].d : 0.f), zb = bc2((P.ground_b == 1) ? P.arm[0].d : 0.f);
-#pragma unroll
-            for (int i = 1; i < J; ++i) {
-                const JointConst q = P.arm[i];
-                const float2 u = fma2(r0, c2[i], mul2(r1, s2[i]));
-                const float2 v = fma2(r1, c2[i], neg2(mul2(r0, s2[i])));
-                tz = fma2(bc2(q.a), u, fma2(bc2(q.d), r2, tz));
-                r0 = u;
-                r1 = fma2(v, bc2(q.ca), mul2(r2, bc2(q.sa)));
-                r2 = fma2(r2, bc2(q.ca), neg2(mul2(v, bc2(q.sa))));
-                if (i + 1 == P.ground_a) za = tz;
-                if (i + 1 == P.ground_b) zb = tz;
-                // advance this joint by 2 delta for the next pair
-                const float2 nc = fma2(c2[i], bc2(cdd[i]), mul2(s2[i], bc2(sdd[i])));
-                s2[i] = fma2(s2[i], bc2(cdd[i]), neg2(mul2(c2[i], bc2(sdd[i]))));
-                c2[i] = nc;
-            }
-            zmin = fminf(zmin, fminf(fminf(za.x, za.y), fminf(zb.x, zb.y)));
-        }
+        // the usual selectors (ground frames J-1 and J) get a copy of the loop with the two z picks
+        // resolved at compile time; any other choice takes the run-time-select copy
+        zmin = (P.ground_a == J - 1 && P.ground_b == J) ? subpose_zmin<J, true>(P, c2, s2, cdd, sdd, iters, zmin)
+                                                        : subpose_zmin<J, false>(P, c2, s2, cdd, sdd, iters, zmin);
     }
     f.zmin = zmin;
 }
@@ -498,8 +526,10 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, long long env,
 // second shared-memory buffer (TMA bulk copy + mbarrier), and tile i-1's
 // observations draining from the other buffer to HBM (TMA bulk store).
 // ---------------------------------------------------------------------------
+template <int ARM> struct StepBuffers { static constexpr int value = (ARM == 0) ? 2 : 1; };
+
 template <int ARM, int X, bool RAND, bool WOBS>
-__global__ void __launch_bounds__(kWarpsPerBlock *kTile, (ARM == 0) ? 7 : 1)
+__global__ void __launch_bounds__(kWarpsPerBlock *kTile, (ARM == 0) ? 7 : 4)
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int J = ARM ? ARM : 4;
@@ -507,9 +537,14 @@ step_kernel(const __grid_constant__ StepParams P) {
     const int x = X ? X : P.n_obj;
     const int rowlen = 3 * x;
     const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
-    unsigned char *tile_base = smem + (size_t)(2 * warp) * P.tile_bytes;   // two buffers, back to back
+    // Tile buffers per warp: two for the reference arm (its kinematics are too short to cover a tile's
+    // HBM latency, so tile i+1 is fetched while tile i is still being turned into observations); one
+    // for the generic chain, whose long kinematics cover the fetch and where the halved footprint
+    // doubles the warps an SM can hold at X = 20.
+    constexpr int NB = StepBuffers<ARM>::value;
+    unsigned char *tile_base = smem + (size_t)(NB * warp) * P.tile_bytes;
     auto tile_buf = [&](int bb) { return reinterpret_cast<float *>(tile_base + (size_t)bb * P.tile_bytes); };
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(2 * kWarpsPerBlock) * P.tile_bytes) + 2 * warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(NB * kWarpsPerBlock) * P.tile_bytes) + NB * warp;
 
     // static round-robin tile schedule: warp w of the grid takes tiles w, w + W, w + 2W, ...  Blocks
     // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
@@ -527,7 +562,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     if (cur >= P.tile_end) return;
     if (lane == 0) {
         mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
+        if (NB == 2) mbar_init(bar + 1, 1);
         mbar_init_fence();
         fetch_points(cur, 0);
     }
@@ -558,7 +593,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 
         // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous
         //    contents, tile i-1's observations, have long been read out by their bulk store)
-        if (nxt >= 0 && lane == 0) {
+        if (NB == 2 && nxt >= 0 && lane == 0) {
             if (WOBS) bulk_wait_read0();
             fetch_points(nxt, b ^ 1);
         }
@@ -668,10 +703,17 @@ step_kernel(const __grid_constant__ StepParams P) {
         }
 
         if (nxt < 0) break;
+        if (NB == 1) {   // single buffer: refill it as soon as the observations have been read out
+            __syncwarp();
+            if (lane == 0) {
+                if (WOBS) bulk_wait_read0();
+                fetch_points(nxt, 0);
+            }
+        }
         cur = nxt;
         nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
         sc = sn;
-        b ^= 1;
+        if (NB == 2) b ^= 1;
         __syncwarp();
     }
     if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
