@@ -106,6 +106,9 @@ int mt_config_init(mt_config *cfg);
 int mt_create(const mt_config *cfg, mt_env **out);
 int mt_destroy(mt_env *env);
 int mt_get_config(const mt_env *env, mt_config *out);
+/* Re-key the on-device Philox streams (actions, objective refresh); takes effect from the next
+ * launch.  Gym-style reset(seed=...). */
+int mt_set_seed(mt_env *env, uint64_t seed);
 
 /* Environment.reset / Multienv.reset -- manytor.py:219-253, 106-109.
  * mask_dev: NULL = all envs, else [N] uint8 selecting the envs to reset.

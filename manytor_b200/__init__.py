@@ -9,6 +9,7 @@ declared in include/manytor_b200.h.  There is no CPU fallback.
 from ._lib import MantorLibraryError, library_path, load as load_library  # noqa: F401
 from .core import ArmSpec, BatchedEnvs, REFERENCE_ARM, UR5_ARM  # noqa: F401
 from . import distributed  # noqa: F401
+from .vector_env import ManyTorVectorEnv  # noqa: F401
 
 __all__ = ["ArmSpec", "BatchedEnvs", "REFERENCE_ARM", "UR5_ARM", "MantorLibraryError", "library_path",
-           "load_library", "distributed"]
+           "load_library", "distributed", "ManyTorVectorEnv"]

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mt_create": (C.c_int, [C.POINTER(MtConfig), C.POINTER(_P)]),
     "mt_destroy": (C.c_int, [_P]),
     "mt_get_config": (C.c_int, [_P, C.POINTER(MtConfig)]),
+    "mt_set_seed": (C.c_int, [_P, C.c_uint64]),
     "mt_reset": (C.c_int, [_P, _P, _P]),
     "mt_observe": (C.c_int, [_P, _P, _P]),
     "mt_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -329,6 +329,11 @@ class BatchedEnvs:
         return dict(goals=goals, joints_coordinates=joints, points=points, alives=alives,
                     total_reward=float(total.value))
 
+    def set_seed(self, seed: int):
+        """Re-key the on-device action / objective streams (gym-style reset(seed=...))."""
+        _lib.check(self._lib.mt_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+
     # -- statistics ---------------------------------------------------------------
     def stats_tensor(self) -> torch.Tensor:
         """MT_STATS_WORDS int64 on the device (sum-reducible across shards)."""

@@ -266,6 +266,14 @@ extern "C" int mt_destroy(mt_env *e) {
     return MT_OK;
 }
 
+extern "C" int mt_set_seed(mt_env *e, uint64_t seed) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    e->cfg.seed = seed;
+    e->base.seed_lo = (uint32_t)seed;
+    e->base.seed_hi = (uint32_t)(seed >> 32);
+    return MT_OK;
+}
+
 extern "C" int mt_get_config(const mt_env *e, mt_config *out) {
     if (!e || !out) return fail(MT_ERR_INVALID, "NULL argument");
     *out = e->cfg;

@@ -149,3 +149,28 @@ def test_million_env_properties(tor):
     assert chk_a == chk_b and a.stats() == b.stats()             # bit-deterministic
     c, _, _, chk_c = run(8)
     assert chk_c != chk_a
+
+
+def test_vector_env_adapter_and_dlpack(tor):
+    """Gymnasium-style 5-tuple API on device tensors; observations are handed over without a copy."""
+    import torch
+    from manytor_b200 import ManyTorVectorEnv
+    n = 4096
+    env = ManyTorVectorEnv(n, 10, max_episode_steps=20, seed=11)
+    obs, info = env.reset(seed=123)
+    assert obs.shape == (n, 30) and obs.is_cuda and info == {}
+    first = obs.clone()
+    ended = torch.zeros(n, dtype=torch.bool, device=obs.device)
+    for t in range(20):
+        obs, reward, terminated, truncated, info = env.step(env.sample_actions())
+        assert reward.shape == (n,) and terminated.dtype == torch.bool and truncated.dtype == torch.bool
+        assert not bool((terminated & truncated).any())
+        ended |= terminated | truncated
+    assert bool(truncated[~terminated].all()) and bool(ended.all())          # step 20 = max_episode_steps
+    via = torch.utils.dlpack.from_dlpack(obs.__dlpack__())
+    assert via.data_ptr() == obs.data_ptr()                                   # zero-copy hand-off
+    # same seed -> same first observations and same trajectory of rewards
+    env2 = ManyTorVectorEnv(n, 10, max_episode_steps=20, seed=999)
+    obs2, _ = env2.reset(seed=123)
+    assert torch.equal(obs2, first)
+    assert env.episode_statistics()["episodes"] >= n
