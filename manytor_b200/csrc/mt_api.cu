@@ -89,7 +89,23 @@ static bool is_reference_arm(const mt_config &c) {
 }
 
 // X values with a specialised (compile-time, packed pair layout) kernel -- keep in sync with pick_kernel
-static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6) && (x == 10 || x == 20); }
+static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6 || arm == kArmUr5) && (x == 10 || x == 20); }
+
+// does the configuration describe the preset arm `id` (table within 1e-6, usual frame selectors)?
+template <int ID>
+static bool is_preset_arm(const mt_config &c) {
+    constexpr int J = ArmJoints<ID>::value;
+    if (c.n_joints != J) return false;
+    for (int i = 0; i < J; ++i) {
+        const JointConst q = Preset<ID>::row(i);
+        const double ca = std::cos((double)c.dh[i][1]), sa = std::sin((double)c.dh[i][1]);
+        const double co = std::cos((double)c.dh[i][3]), so = std::sin((double)c.dh[i][3]);
+        if (std::fabs(c.dh[i][0] - q.a) > 1e-6 || std::fabs(c.dh[i][2] - q.d) > 1e-6 || std::fabs(ca - q.ca) > 1e-6 ||
+            std::fabs(sa - q.sa) > 1e-6 || std::fabs(co - q.co) > 1e-6 || std::fabs(so - q.so) > 1e-6)
+            return false;
+    }
+    return c.obs_frame == J - 1 && c.ground_frame_a == J - 1 && c.ground_frame_b == J && c.catch_frame == J;
+}
 
 static double snap(double v) { return std::fabs(v) < 1e-12 ? 0.0 : (std::fabs(std::fabs(v) - 1.0) < 1e-12 ? (v > 0 ? 1.0 : -1.0) : v); }
 
@@ -215,7 +231,11 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->n = cfg->n_envs;
     e->n_tiles = (e->n + kTile - 1) / kTile;
     e->n_pad = e->n_tiles * kTile;
-    e->arm = (cfg->fk_mode != 1 && is_reference_arm(*cfg)) ? 0 : cfg->n_joints;
+    e->arm = cfg->n_joints;                                   // run-time DH table
+    if (cfg->fk_mode != 1) {
+        if (is_reference_arm(*cfg)) e->arm = 0;               // closed form
+        else if (is_preset_arm<kArmUr5>(*cfg)) e->arm = kArmUr5;  // compile-time table
+    }
     const size_t np = (size_t)e->n_pad, J = cfg->n_joints, X = cfg->n_obj;
 #define ALLOC(ptr, bytes)                                        \
     do {                                                         \
@@ -288,7 +308,7 @@ __device__ __forceinline__ void pose_of(const StepParams &P, int arm, const floa
     switch (arm) {
         case 0: ref_arm(g, g, 1, 0.f, f, jout); break;
 #define MT_CASE(JJ) case JJ: { StepParams Q = P; Q.substeps = 1; generic_arm<JJ>(Q, g, g, f, jout); } break;
-        MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8)
+        MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8) MT_CASE(kArmUr5)
 #undef MT_CASE
     }
 }
@@ -502,6 +522,7 @@ static StepFn pick_kernel(int arm, int x, bool rnd, bool wobs) {
         case 6: return pick_x<6>(x, rnd, wobs);
         case 7: return pick_flags<7, 0>(rnd, wobs);
         case 8: return pick_flags<8, 0>(rnd, wobs);
+        case kArmUr5: return pick_x<kArmUr5>(x, rnd, wobs);
     }
     return nullptr;
 }

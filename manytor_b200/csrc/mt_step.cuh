@@ -22,6 +22,8 @@
 #include "mt_math.cuh"
 #include "mt_ptx.cuh"
 
+#include <type_traits>
+
 namespace mt {
 
 constexpr int kWarpsPerBlock = 4;
@@ -187,93 +189,176 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
     f.zmin = zmin;
 }
 
+// ---------------------------------------------------------------------------
+// Generic J-joint DH chain -- the reference's "pluggable fk" (README.md:20, manytor.py:126-127).
+//
+// ARM template values: 0 = reference arm closed form (above); 2..8 = J joints with the DH table
+// read at run time from the kernel parameters; >= 100 = a PRESET arm whose table is a constexpr
+// in this header (ARM % 100 joints), so every row's a = 0 / d = 0 / alpha in {0, +-pi/2} folds at
+// compile time and most of the chain disappears.  Plugging in a new arm at full speed = adding a
+// Preset<> specialisation here and a case in pick_kernel (mt_api.cu); any other table still runs
+// through the run-time path.  Presets assume the usual frame selectors (obs J-1, ground J-1 and J,
+// catch J); mt_create only picks a preset when the configuration says so.
+// ---------------------------------------------------------------------------
+constexpr int kArmUr5 = 106;
+
+template <int ARM> struct ArmJoints { static constexpr int value = ARM == 0 ? 4 : (ARM >= 100 ? ARM % 100 : ARM); };
+
+template <int ARM> struct Preset {
+    static constexpr bool value = false;
+    __host__ __device__ static constexpr JointConst row(int) { return JointConst{0.f, 0.f, 1.f, 0.f, 1.f, 0.f}; }
+};
+// UR5 (BASELINE.json config 5), metres: (a, d, cos alpha, sin alpha, cos offset, sin offset)
+template <> struct Preset<kArmUr5> {
+    static constexpr bool value = true;
+    __host__ __device__ static constexpr JointConst row(int i) {
+        switch (i) {
+            case 0: return JointConst{0.f, 0.089159f, 0.f, 1.f, 1.f, 0.f};
+            case 1: return JointConst{-0.425f, 0.f, 1.f, 0.f, 1.f, 0.f};
+            case 2: return JointConst{-0.39225f, 0.f, 1.f, 0.f, 1.f, 0.f};
+            case 3: return JointConst{0.f, 0.10915f, 0.f, 1.f, 1.f, 0.f};
+            case 4: return JointConst{0.f, 0.09465f, 0.f, -1.f, 1.f, 0.f};
+            default: return JointConst{0.f, 0.0823f, 1.f, 0.f, 1.f, 0.f};
+        }
+    }
+};
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// scalar / packed arithmetic under one name, so a row update is written once
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float2 vfma(float2 a, float2 b, float2 c) { return fma2(a, b, c); }
+__device__ __forceinline__ float vmul(float a, float b) { return a * b; }
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return mul2(a, b); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float2 vneg(float2 a) { return neg2(a); }
+template <class T> __device__ __forceinline__ T vbc(float x);
+template <> __device__ __forceinline__ float vbc<float>(float x) { return x; }
+template <> __device__ __forceinline__ float2 vbc<float2>(float x) { return bc2(x); }
+
+template <int ARM, int I>
+__device__ __forceinline__ JointConst joint_of(const StepParams &P) {
+    if constexpr (Preset<ARM>::value) return Preset<ARM>::row(I);
+    else return P.arm[I];
+}
+
+// Push the row vector (r0, r1, r2 | t) of the accumulated transform through DH row I, whose joint
+// angle has cosine c and sine s:  row <- row * [Rz(theta) Tz(d) Tx(a) Rx(alpha)]  (manytor.py:25-32).
+template <int ARM, int I, class T>
+__device__ __forceinline__ void push_row(const StepParams &P, T &r0, T &r1, T &r2, T &t, T c, T s) {
+    const T u = vfma(r0, c, vmul(r1, s));
+    const T v = vfma(r1, c, vneg(vmul(r0, s)));
+    const T o = r2;
+    if constexpr (Preset<ARM>::value) {
+        constexpr JointConst q = Preset<ARM>::row(I);
+        if constexpr (q.a != 0.f) t = vfma(vbc<T>(q.a), u, t);
+        if constexpr (q.d != 0.f) t = vfma(vbc<T>(q.d), o, t);
+        if constexpr (q.sa == 0.f && q.ca == 1.f) { r1 = v; }
+        else if constexpr (q.sa == 0.f && q.ca == -1.f) { r1 = vneg(v); r2 = vneg(o); }
+        else if constexpr (q.ca == 0.f && q.sa == 1.f) { r1 = o; r2 = vneg(v); }
+        else if constexpr (q.ca == 0.f && q.sa == -1.f) { r1 = vneg(o); r2 = v; }
+        else {
+            r1 = vfma(v, vbc<T>(q.ca), vmul(o, vbc<T>(q.sa)));
+            r2 = vfma(o, vbc<T>(q.ca), vneg(vmul(v, vbc<T>(q.sa))));
+        }
+    } else {
+        const JointConst q = P.arm[I];
+        t = vfma(vbc<T>(q.a), u, vfma(vbc<T>(q.d), o, t));
+        r1 = vfma(v, vbc<T>(q.ca), vmul(o, vbc<T>(q.sa)));
+        r2 = vfma(o, vbc<T>(q.ca), vneg(vmul(v, vbc<T>(q.sa))));
+    }
+    r0 = u;
+}
+
 // z of the two ground frames at two sub-poses per iteration (lanes .x/.y), minimum over `iters`
-// iterations.  The z row e_z^T A_1 .. A_k does not depend on joint 0's angle: it starts as the
-// constant (0, sin a0, cos a0 | d0) and is pushed through joints 1 .. J-1.
-template <int J, bool STD>
+// iterations.  The z row e_z^T A_1 .. A_k does not depend on joint 0's angle: after joint 0 it is the
+// constant (0, sin a0, cos a0 | d0), and pushing THAT through joint 1 needs no r0 terms.
+template <int ARM, bool STD>
 __device__ __forceinline__ float subpose_zmin(const StepParams &P, float2 *c2, float2 *s2, const float *cdd,
                                               const float *sdd, int iters, float zmin) {
-    const float sa0 = P.arm[0].sa, ca0 = P.arm[0].ca, d0 = P.arm[0].d;
+    constexpr int J = ArmJoints<ARM>::value;
+    const JointConst q0 = joint_of<ARM, 0>(P);
     for (int it = 0; it < iters; ++it) {
         float2 r0, r1, r2, tz;
-        float2 za = bc2(d0), zb = bc2(d0);          // frame 1 (only reachable through run-time selectors or J = 2)
+        float2 za = bc2(q0.d), zb = bc2(q0.d);     // frame 1 (only reachable through run-time selectors or J = 2)
         if (!STD) {
-            za = bc2((P.ground_a == 1) ? d0 : 0.f);
-            zb = bc2((P.ground_b == 1) ? d0 : 0.f);
+            za = bc2((P.ground_a == 1) ? q0.d : 0.f);
+            zb = bc2((P.ground_b == 1) ? q0.d : 0.f);
         }
-#pragma unroll
-        for (int i = 1; i < J; ++i) {
-            const JointConst q = P.arm[i];
-            float2 u, v;
-            if (i == 1) {                           // r0 = 0, r1 = sa0, r2 = ca0 are constants here
-                u = mul2(bc2(sa0), s2[1]);
-                v = mul2(bc2(sa0), c2[1]);
-                tz = fma2(bc2(q.a), u, bc2(fmaf(q.d, ca0, d0)));
-                r1 = fma2(v, bc2(q.ca), bc2(ca0 * q.sa));
-                r2 = fma2(v, bc2(-q.sa), bc2(ca0 * q.ca));
+        static_for<1, J>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (i == 1) {                 // row entering joint 1 is constant with r0 = 0
+                const JointConst q = joint_of<ARM, 1>(P);
+                const float2 u = mul2(bc2(q0.sa), s2[1]);
+                const float2 v = mul2(bc2(q0.sa), c2[1]);
+                tz = fma2(bc2(q.a), u, bc2(fmaf(q.d, q0.ca, q0.d)));
+                r1 = fma2(v, bc2(q.ca), bc2(q0.ca * q.sa));
+                r2 = fma2(v, bc2(-q.sa), bc2(q0.ca * q.ca));
+                r0 = u;
             } else {
-                u = fma2(r0, c2[i], mul2(r1, s2[i]));
-                v = fma2(r1, c2[i], neg2(mul2(r0, s2[i])));
-                tz = fma2(bc2(q.a), u, fma2(bc2(q.d), r2, tz));
-                const float2 r2o = r2;
-                r2 = fma2(r2o, bc2(q.ca), neg2(mul2(v, bc2(q.sa))));
-                r1 = fma2(v, bc2(q.ca), mul2(r2o, bc2(q.sa)));
+                push_row<ARM, i, float2>(P, r0, r1, r2, tz, c2[i], s2[i]);
             }
-            r0 = u;
             if (STD ? (i + 1 == J - 1) : (i + 1 == P.ground_a)) za = tz;
             if (STD ? (i + 1 == J) : (i + 1 == P.ground_b)) zb = tz;
             // advance this joint by 2 delta for the next pair of sub-poses
             const float2 nc = fma2(c2[i], bc2(cdd[i]), mul2(s2[i], bc2(sdd[i])));
             s2[i] = fma2(s2[i], bc2(cdd[i]), neg2(mul2(c2[i], bc2(sdd[i]))));
             c2[i] = nc;
-        }
+        });
         zmin = fminf(zmin, fminf(fminf(za.x, za.y), fminf(zb.x, zb.y)));
     }
     return zmin;
 }
 
-// Generic J-joint DH chain (the reference's "pluggable fk", README.md:20).
-// Final pose: 3x4 affine prefix products, origins of every frame.  Sub-poses:
-// only the z row e_z^T A_1 ... A_k is propagated (10 FMA-class ops per joint);
-// it does not depend on the first joint's angle.
-template <int J>
+// Final pose: 3x4 affine prefix products give the origin of every frame (manytor.py:188-189).
+// Sub-poses: only the z row is propagated, two sub-poses per packed iteration.
+template <int ARM>
 __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g, const float *a, Frames &f,
                                             float *jout /* J*3 floats or nullptr */) {
+    constexpr int J = ArmJoints<ARM>::value;
+    constexpr bool kPreset = Preset<ARM>::value;
+    const int obs_frame = kPreset ? J - 1 : P.obs_frame, catch_frame = kPreset ? J : P.catch_frame;
+    const int ground_a = kPreset ? J - 1 : P.ground_a, ground_b = kPreset ? J : P.ground_b;
     float c[J], s[J];
-#pragma unroll
-    for (int i = 0; i < J; ++i) {
+    static_for<0, J>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
         float si, ci;
         sincos_deg(a[i], si, ci);
-        c[i] = fmaf(ci, P.arm[i].co, -(si * P.arm[i].so));
-        s[i] = fmaf(si, P.arm[i].co, ci * P.arm[i].so);
-    }
-    // rows of the accumulated transform: R (3x3) and t (3)
-    float R[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
-    float t[3] = {0.f, 0.f, 0.f};
+        const JointConst q = joint_of<ARM, i>(P);
+        if (kPreset && q.so == 0.f && q.co == 1.f) {       // no theta offset on this row
+            c[i] = ci; s[i] = si;
+        } else {
+            c[i] = fmaf(ci, q.co, -(si * q.so));
+            s[i] = fmaf(si, q.co, ci * q.so);
+        }
+    });
+    // rows of the accumulated transform after joint 0 = the DH matrix of row 0 itself
+    const JointConst q0 = joint_of<ARM, 0>(P);
+    float R[3][3] = {{c[0], -s[0] * q0.ca, s[0] * q0.sa}, {s[0], c[0] * q0.ca, -c[0] * q0.sa}, {0.f, q0.sa, q0.ca}};
+    float t[3] = {q0.a * c[0], q0.a * s[0], q0.d};
     float zA = 0.f, zB = 0.f;
     if (jout) { jout[0] = 0.f; jout[1] = 0.f; jout[2] = 0.f; }
-    if (P.obs_frame == 0) { f.anchor[0] = f.anchor[1] = f.anchor[2] = 0.f; }
-    if (P.catch_frame == 0) { f.catcher[0] = f.catcher[1] = f.catcher[2] = 0.f; }
+    if (obs_frame == 0) { f.anchor[0] = f.anchor[1] = f.anchor[2] = 0.f; }
+    if (catch_frame == 0) { f.catcher[0] = f.catcher[1] = f.catcher[2] = 0.f; }
+    static_for<0, J>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        if constexpr (i > 0) {
 #pragma unroll
-    for (int i = 0; i < J; ++i) {
-        const JointConst q = P.arm[i];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            float u = fmaf(R[r][0], c[i], R[r][1] * s[i]);
-            float v = fmaf(R[r][1], c[i], -(R[r][0] * s[i]));
-            float r2 = R[r][2];
-            t[r] = fmaf(q.a, u, fmaf(q.d, r2, t[r]));
-            R[r][0] = u;
-            R[r][1] = fmaf(v, q.ca, r2 * q.sa);
-            R[r][2] = fmaf(r2, q.ca, -(v * q.sa));
+            for (int r = 0; r < 3; ++r) push_row<ARM, i, float>(P, R[r][0], R[r][1], R[r][2], t[r], c[i], s[i]);
         }
         const int frame = i + 1;
-        if (frame == P.obs_frame) { f.anchor[0] = t[0]; f.anchor[1] = t[1]; f.anchor[2] = t[2]; }
-        if (frame == P.catch_frame) { f.catcher[0] = t[0]; f.catcher[1] = t[1]; f.catcher[2] = t[2]; }
-        if (frame == P.ground_a) zA = t[2];
-        if (frame == P.ground_b) zB = t[2];
+        if (frame == obs_frame) { f.anchor[0] = t[0]; f.anchor[1] = t[1]; f.anchor[2] = t[2]; }
+        if (frame == catch_frame) { f.catcher[0] = t[0]; f.catcher[1] = t[1]; f.catcher[2] = t[2]; }
+        if (frame == ground_a) zA = t[2];
+        if (frame == ground_b) zB = t[2];
         if (jout && frame >= 2) { jout[(frame - 1) * 3 + 0] = t[0]; jout[(frame - 1) * 3 + 1] = t[1]; jout[(frame - 1) * 3 + 2] = t[2]; }
-    }
+    });
     float zmin = fminf(zA, zB);
     // Interior sub-poses k = 1 .. M (k steps back from the final pose), TWO per iteration: the .x
     // lane of every packed value is sub-pose k, the .y lane sub-pose k+1, and both advance by
@@ -298,8 +383,8 @@ __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g,
         const int iters = (M + 1) >> 1;
         // the usual selectors (ground frames J-1 and J) get a copy of the loop with the two z picks
         // resolved at compile time; any other choice takes the run-time-select copy
-        zmin = (P.ground_a == J - 1 && P.ground_b == J) ? subpose_zmin<J, true>(P, c2, s2, cdd, sdd, iters, zmin)
-                                                        : subpose_zmin<J, false>(P, c2, s2, cdd, sdd, iters, zmin);
+        if (kPreset || (ground_a == J - 1 && ground_b == J)) zmin = subpose_zmin<ARM, true>(P, c2, s2, cdd, sdd, iters, zmin);
+        else if constexpr (!kPreset) zmin = subpose_zmin<ARM, false>(P, c2, s2, cdd, sdd, iters, zmin);
     }
     f.zmin = zmin;
 }
@@ -532,7 +617,7 @@ template <int ARM, int X, bool RAND, bool WOBS>
 __global__ void __launch_bounds__(kWarpsPerBlock *kTile, (ARM == 0) ? 7 : 4)
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int J = ARM ? ARM : 4;
+    constexpr int J = ArmJoints<ARM>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x = X ? X : P.n_obj;
     const int rowlen = 3 * x;
@@ -588,7 +673,7 @@ step_kernel(const __grid_constant__ StepParams P) {
         float jbuf[J * 3];
         float *jout = P.joints ? jbuf : nullptr;
         if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, jout);
-        else generic_arm<J>(P, sc.g, sc.a, f, jout);
+        else generic_arm<ARM>(P, sc.g, sc.a, f, jout);
         const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
 
         // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous

@@ -116,10 +116,12 @@ def test_generic_chain_on_reference_arm(mt):
     assert rep.ok(), rep.notes[:5]
 
 
-def test_config5_ur5_six_dof(mt):
-    """BASELINE.json config 5: 6-DOF UR5-style chain, x = 20."""
+@pytest.mark.parametrize("fk_mode", [0, 1])
+def test_config5_ur5_six_dof(mt, fk_mode):
+    """BASELINE.json config 5: 6-DOF UR5-style chain, x = 20.  fk_mode 0 picks the compile-time
+    preset table (constant-folded chain), fk_mode 1 forces the run-time DH table path."""
     n, x = 1024, 20
-    env = mt.BatchedEnvs(n, x, arm=mt.UR5_ARM, device=0)
+    env = mt.BatchedEnvs(n, x, arm=mt.UR5_ARM, device=0, fk_mode=fk_mode)
     ora = OracleEnvs(n, x, spec=UR5_ARM)
     rng = np.random.RandomState(21)
     env.reset()
