@@ -54,13 +54,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, period_ms: int = 200):
+        self.gpu, self.proc, self.lines, self.period_ms = gpu_index, None, [], int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", str(self.period_ms)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -243,7 +243,7 @@ def run_gpu(args) -> None:
         return e0.elapsed_time(e1), env.launch_count - l0
 
     # ---- headline: K x mt_step, actions from HBM, obs written (309 B/env-step) ----------
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, args.clock_period_ms) if rank == 0 and args.clock_period_ms > 0 else None
     stats_holder = {}
 
     def step_fn(i):
@@ -255,22 +255,48 @@ def run_gpu(args) -> None:
         for i in range(200):
             step_fn(i)
         torch.cuda.synchronize()
+    # The K timed steps are K launches of the step kernel either way; by default they are submitted
+    # as ONE CUDA graph (captured untimed, each node its own action buffer), which is how an RL loop
+    # that graphs policy + env drives it and removes the ~3 us per-launch gap of stream launches.
+    graph = None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(stream)
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    step_fn(i)
+            stream.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(K):
+                    step_fn(W + i)
+        except Exception as ex:
+            print(f"bench: CUDA graph capture failed ({ex}); timing stream launches", file=sys.stderr)
+            graph = None
     if sampler:
         sampler.start()
     for i in range(W):
         step_fn(i)
+    if graph is not None:
+        graph.replay()                            # untimed: first replay uploads the graph
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     l0 = env.launch_count
     e0.record(stream)
-    for i in range(K):
-        step_fn(W + i)
+    if graph is not None:
+        graph.replay()                            # exactly K steps
+    else:
+        for i in range(K):
+            step_fn(W + i)
     e1.record(stream)
     st = env.stats_tensor()                       # end-of-rollout statistics ...
     mtd.allreduce_stats(st)                       # ... one NCCL all-reduce (config 4)
     e2.record(stream)
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-    launches_timed = env.launch_count - l0
+    # my kernels inside the timed region: K step kernels (graph nodes or stream launches) + 1 stats kernel
+    launches_timed = (K + 1) if graph is not None else env.launch_count - l0
     timed_ms_local = e0.elapsed_time(e2)
     # K steps last only a few ms, far below nvidia-smi's sampling period: keep the same step
     # loop running (untimed) so the clock sampler sees the load the timed region ran under
@@ -281,7 +307,7 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["note"] = (f"sampled every 50 ms from just before the warm-up steps, through the {timed_ms_local:.1f} ms "
+        clocks["note"] = (f"sampled every {args.clock_period_ms} ms from just before the warm-up steps, through the {timed_ms_local:.1f} ms "
                           f"timed region, and over a {args.clock_probe_s:.1f} s untimed continuation of the same step loop")
     launches = launches_timed
     ms_total = mtd.max_over_ranks(e0.elapsed_time(e2), dev)
@@ -300,7 +326,12 @@ def run_gpu(args) -> None:
     modes["rollout_random_in_kernel_actions"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, True)}
     ms, _ = timed(lambda i: env.rollout_random(1, write_obs=False), KM, 3)
     modes["rollout_random_no_obs_write"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, False)}
+    # the same steps as individual stream launches from Python (no graph)
+    ms, _ = timed(step_fn, KM, 3)
+    modes["step_hbm_actions_stream_launches"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": B}
     for m in modes.values():
+        if "error" in m:
+            continue
         m["hbm_gbs"] = m["env_steps_per_s"] * m["bytes_per_env_step"] / 1e9
         m["frac_of_peak"] = m["hbm_gbs"] / peak
 
@@ -335,6 +366,7 @@ def run_gpu(args) -> None:
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "n_joints": 4, "n_obj": OBJ, "horizon": HORIZON,
                        "terminate_on_ground": False, "auto_reset": True, "actions": "uniform integer degrees in [-180,180), read from HBM [N][4] fp32",
+                       "submission": "one K-node CUDA graph" if graph is not None else "K stream launches",
                        "burn_in_steps": args.burn_in,
                        "l2": f"working set {(n * (B + 8 * 4)) / 2**20:.0f} MiB per step > 126 MiB L2 (inputs larger than L2, no flush needed)",
                        "parallelism": f"env-sharded x{world}, no per-step collective, 1 stats all-reduce"},
@@ -359,11 +391,13 @@ def run_gpu(args) -> None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--clock-warm-s", type=float, default=1.0, help="untimed seconds of the step loop before warm-up")
     ap.add_argument("--clock-probe-s", type=float, default=1.0, help="untimed continuation for the clock sampler")
+    ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period (0 = no sampler)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time K stream launches instead of one K-node CUDA graph")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--burn-in", type=int, default=HORIZON,
                     help="untimed random-action steps before warm-up so episodes reach their steady state")

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <unordered_map>
 
 #include "mt_step.cuh"
 
@@ -58,6 +59,7 @@ struct mt_env {
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;
     int num_sms = 0;
+    std::unordered_map<const void *, int> blocks_per_sm;   // occupancy of each step-kernel variant, queried once
     const float *obj_stream = nullptr;
     int32_t obj_sets = 0;
     unsigned long long step_index = 0;
@@ -552,16 +554,32 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
     const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
     const size_t smem = nb * kWarpsPerBlock * P.tile_bytes + nb * kWarpsPerBlock * sizeof(uint64_t);
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kWarpsPerBlock * kTile, smem));
-    if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
+    auto hit = e->blocks_per_sm.find((const void *)fn);
+    if (hit != e->blocks_per_sm.end()) {
+        per_sm = hit->second;
+    } else {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kWarpsPerBlock * kTile, smem));
+        if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
+        e->blocks_per_sm[(const void *)fn] = per_sm;
+    }
     const long long tiles = t1 - t0;
     const long long want = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const long long cap = (long long)per_sm * e->num_sms;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    fn<<<grid, kWarpsPerBlock * kTile, smem, st>>>(P);
-    CU(cudaGetLastError());
+    // programmatic dependent launch: see griddep_wait() in mt_ptx.cuh
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kWarpsPerBlock * kTile);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&lc, fn, P));
     e->launches++;
     return MT_OK;
 }

@@ -125,6 +125,15 @@ __device__ __forceinline__ void bulk_store_hint(void *dst_gmem, const void *src_
                  : "memory");
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// Consecutive step launches are data dependent (step t+1 reads the state step t wrote), but the
+// next launch's block scheduling, shared-memory carve-up and barrier setup are not.  With the
+// launch attribute cudaLaunchAttributeProgrammaticStreamSerialization the next grid may become
+// resident as soon as this one has let it (launch_dependents, issued at kernel entry) and SM
+// resources free up; it then parks at griddep_wait() until this grid has completed and flushed.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // order generic-proxy writes to shared memory before later async-proxy (TMA) reads
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

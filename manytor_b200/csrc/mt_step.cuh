@@ -644,13 +644,15 @@ step_kernel(const __grid_constant__ StepParams P) {
     };
 
     long long cur = first;
+    griddep_launch_dependents();            // the next step's grid may start taking free SM slots
     if (cur >= P.tile_end) return;
     if (lane == 0) {
         mbar_init(bar, 1);
         if (NB == 2) mbar_init(bar + 1, 1);
         mbar_init_fence();
-        fetch_points(cur, 0);
     }
+    griddep_wait();                         // ... but nothing touches the state before the previous step is complete
+    if (lane == 0) fetch_points(cur, 0);
     __syncwarp();
     TileScalars<J> sc;
     load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
