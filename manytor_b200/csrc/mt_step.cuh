@@ -180,8 +180,9 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
         for (int p = 1; p < substeps; ++p) {
             q12.back();
             qAB.back();
-            const float2 sd = fma2(bc2(qAB.x.y), pm, bc2(qAB.x.x));     // (uA + uB, uA - uB)
-            const float t = fmaf(q12.x.y, sd.y, q12.x.x + sd.x);
+            // ee_z - 4.3 = u1 + (uA + uB) + cos(th2) (uA - uB); scalar here on purpose: a packed
+            // (sum, difference) needs a (1, -1) operand pair that ptxas re-creates every iteration
+            const float t = fmaf(q12.x.y, qAB.x.x - qAB.x.y, q12.x.x + (qAB.x.x + qAB.x.y));
             m = fminf(m, fminf(q12.x.x, t));
         }
         zmin = fminf(zmin, m + H);
