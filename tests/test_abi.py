@@ -103,3 +103,31 @@ def test_library_is_sm100a_with_tma(lib):
     assert "sm_100a" in elf
     sass = subprocess.run([cu, "-sass", _lib.library_path()], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass
+
+
+def _build_c_host(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "c_host")
+    lib_dir = os.path.dirname(_lib.library_path())
+    cmd = [gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_host.c"),
+           "-o", exe, "-L", lib_dir, "-lmanytor_b200", f"-Wl,-rpath,{lib_dir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_plain_c_host_links_against_the_abi(lib, tmp_path):
+    """examples/c_host.c: a host with no CUDA/torch/Python dependency compiles against the header
+    (-Wall -Werror) and links the shared library; without a GPU it must fail loudly, not fall back."""
+    import subprocess
+    import torch
+    exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe, "64", "2"], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert res.returncode == 0, res.stderr
+    else:
+        assert res.returncode == 1 and "no CPU fallback" in res.stderr

@@ -174,3 +174,13 @@ def test_vector_env_adapter_and_dlpack(tor):
     obs2, _ = env2.reset(seed=123)
     assert torch.equal(obs2, first)
     assert env.episode_statistics()["episodes"] >= n
+
+
+def test_plain_c_host_runs(tor, tmp_path):
+    """The C-ABI used from plain C (examples/c_host.c): test_multi.py's loop with host buffers."""
+    import subprocess
+    from test_abi import _build_c_host
+    exe = _build_c_host(tmp_path)
+    res = subprocess.run([exe, "5000", "60"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr + res.stdout
+    assert "envs 5000 steps 60" in res.stdout and "300000 env-steps" in res.stdout
