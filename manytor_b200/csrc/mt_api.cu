@@ -91,7 +91,7 @@ static bool is_reference_arm(const mt_config &c) {
 }
 
 // X values with a specialised (compile-time, packed pair layout) kernel -- keep in sync with pick_kernel
-static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6 || arm == kArmUr5) && (x == 10 || x == 20); }
+static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6 || arm >= 100) && (x == 10 || x == 20); }
 
 // does the configuration describe the preset arm `id` (table within 1e-6, usual frame selectors)?
 template <int ID>
@@ -236,7 +236,9 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->arm = cfg->n_joints;                                   // run-time DH table
     if (cfg->fk_mode != 1) {
         if (is_reference_arm(*cfg)) e->arm = 0;               // closed form
-        else if (is_preset_arm<kArmUr5>(*cfg)) e->arm = kArmUr5;  // compile-time table
+#define MT_MATCH(ID) else if (is_preset_arm<ID>(*cfg)) e->arm = ID;   /* compile-time table */
+        MT_FOR_EACH_PRESET_ARM(MT_MATCH)
+#undef MT_MATCH
     }
     const size_t np = (size_t)e->n_pad, J = cfg->n_joints, X = cfg->n_obj;
 #define ALLOC(ptr, bytes)                                        \
@@ -310,7 +312,8 @@ __device__ __forceinline__ void pose_of(const StepParams &P, int arm, const floa
     switch (arm) {
         case 0: ref_arm(g, g, 1, 0.f, f, jout); break;
 #define MT_CASE(JJ) case JJ: { StepParams Q = P; Q.substeps = 1; generic_arm<JJ>(Q, g, g, f, jout); } break;
-        MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8) MT_CASE(kArmUr5)
+        MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8)
+        MT_FOR_EACH_PRESET_ARM(MT_CASE)
 #undef MT_CASE
     }
 }
@@ -524,7 +527,9 @@ static StepFn pick_kernel(int arm, int x, bool rnd, bool wobs) {
         case 6: return pick_x<6>(x, rnd, wobs);
         case 7: return pick_flags<7, 0>(rnd, wobs);
         case 8: return pick_flags<8, 0>(rnd, wobs);
-        case kArmUr5: return pick_x<kArmUr5>(x, rnd, wobs);
+#define MT_PICK(ID) case ID: return pick_x<ID>(x, rnd, wobs);
+        MT_FOR_EACH_PRESET_ARM(MT_PICK)
+#undef MT_PICK
     }
     return nullptr;
 }

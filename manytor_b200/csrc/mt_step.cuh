@@ -202,6 +202,9 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
 // catch J); mt_create only picks a preset when the configuration says so.
 // ---------------------------------------------------------------------------
 constexpr int kArmUr5 = 106;
+// every preset arm, once: mt_api.cu expands this list for detection (is_preset_arm), kernel
+// dispatch (pick_kernel) and the helper kernels, so adding an arm = one Preset<> + one line here
+#define MT_FOR_EACH_PRESET_ARM(X) X(kArmUr5)
 
 template <int ARM> struct ArmJoints { static constexpr int value = ARM == 0 ? 4 : (ARM >= 100 ? ARM % 100 : ARM); };
 

@@ -397,3 +397,81 @@ def test_state_roundtrip_and_dead_points(mt):
     np.testing.assert_array_equal(f["goals"], goals[5])
     from oracle.manytor_oracle import joints_coordinates
     np.testing.assert_allclose(f["joints_coordinates"], joints_coordinates(goals[5].astype(np.float64)), atol=5.6e-4)
+
+
+# --------------------------------------------------------------------------
+# more edge cases of the configuration space
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("substeps,fk_mode", [(2, 0), (8, 0), (24, 0), (25, 1), (8, 1), (9, 1), (2, 1)])
+def test_other_substep_counts(mt, substeps, fk_mode):
+    """`step = 25` is a literal in the reference (manytor.py:178); the kernels take it as a parameter
+    (even and odd numbers of interior sub-poses take different pairings in the generic chain)."""
+    import dataclasses
+    n, x = 300, 10
+    spec = dataclasses.replace(REFERENCE_ARM, substeps=substeps)
+    env = mt.BatchedEnvs(n, x, device=0, substeps=substeps, fk_mode=fk_mode)
+    ora = OracleEnvs(n, x, spec=spec)
+    pts = ref_points(n, x, seed=substeps)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(substeps + 100 * fk_mode)
+    rep = lockstep(env, ora, spec, lambda t: rng.randint(-180, 180, size=(n, 4)), 30)
+    assert rep.ok(), rep.notes[:5]
+
+
+def test_non_standard_frame_selectors(mt):
+    """Run-time frame selectors of the generic chain: observe from frame 2, ground-test frames 2 and 4,
+    catch with frame 3 (the reference hard-codes 3 / 3,4 / 4, manytor.py:143,162,191)."""
+    import dataclasses
+    n, x = 256, 6
+    spec = dataclasses.replace(REFERENCE_ARM, obs_frame=2, ground_frames=(2, 4), catch_frame=3)
+    arm = mt.ArmSpec(dh=mt.REFERENCE_ARM.dh, obs_frame=2, ground_frames=(2, 4), catch_frame=3)
+    env = mt.BatchedEnvs(n, x, arm=arm, device=0)
+    ora = OracleEnvs(n, x, spec=spec)
+    pts = ref_points(n, x, seed=77)
+    ora.reset(points=pts)
+    env.reset()
+    env.set_points(pts)
+    rng = np.random.RandomState(78)
+    rep = lockstep(env, ora, spec, lambda t: rng.randint(-180, 180, size=(n, 4)), 30)
+    assert rep.ok(), rep.notes[:5]
+
+
+@pytest.mark.parametrize("n,x,tog", [(77, 32, False), (45, 10, True), (130, 3, False)])
+def test_auto_reset_tail_tiles_and_ground_termination(mt, n, x, tog):
+    """In-kernel reset on ragged shards, the maximum objective count, and README-style termination
+    on ground contact: every reset must restore the reference's reset() state (manytor.py:219-241)."""
+    horizon = 6
+    env = mt.BatchedEnvs(n, x, device=0, auto_reset=True, horizon=horizon, terminate_on_ground=tog, seed=n)
+    env.reset()
+    ora = OracleEnvs(n, x, terminate_on_ground=tog)
+    ora.reset(points=env.get_points(zero_dead=False).cpu().numpy().astype(np.float64))
+    rng = np.random.RandomState(x)
+    episodes = 0
+    for t in range(40):
+        act = rng.randint(-180, 180, size=(n, 4)).astype(np.float64)
+        obs, rew, done = (o.cpu().numpy() for o in env.step(act.astype(np.float32)))
+        r = ora.step(act)
+        near = (r.ground_margin < 1e-3) | (np.where(ora.alive | r.alive, np.abs(r.catch_margin), np.inf).min(axis=1) < 1e-3)
+        trunc = (ora.ep_len >= horizon) & ~r.done
+        ok = (rew.astype(np.int64) == r.reward) & ((done & 1).astype(bool) == r.done) & ((done & 2).astype(bool) == trunc)
+        assert (ok | near).all()
+        ended = (done != 0)
+        st = env.get_state()
+        if ended.any():
+            episodes += int(ended.sum())
+            assert np.all(st["goals"].cpu().numpy()[ended] == 0) and np.all(st["ep_len"].cpu().numpy()[ended] == 0)
+            assert np.all(alive_bits_to_matrix(st["alive"].cpu().numpy(), x)[ended])
+            pts = env.get_points(zero_dead=False).cpu().numpy().astype(np.float64)
+            assert (np.linalg.norm(pts[ended], axis=-1) <= 51.3 * (1 + 1e-6)).all() and (pts[ended][..., 2] >= 0).all()
+        # follow the device (its sampler drew the fresh objectives; flips near a threshold re-sync too)
+        ora.reset(mask=ended, points=env.get_points(zero_dead=False).cpu().numpy().astype(np.float64))
+        keep = ~ended
+        ora.goals[keep] = st["goals"].cpu().numpy()[keep]
+        ora.alive[keep] = alive_bits_to_matrix(st["alive"].cpu().numpy(), x)[keep]
+        ora.total_reward[keep] = st["total_reward"].cpu().numpy()[keep]
+        ora.ep_len[keep] = st["ep_len"].cpu().numpy()[keep]
+        from oracle.manytor_oracle import joints_coordinates
+        ora.joints = joints_coordinates(ora.goals)
+    assert env.stats()["episodes"] == episodes and episodes >= n * 5
