@@ -74,7 +74,9 @@ typedef struct mt_config {
     int32_t auto_reset;            /* 1: envs that end are reset inside the step kernel   */
     int32_t obs_after_reset;       /* with auto_reset: 0 = emit obs2 of the ending step,
                                       1 = emit the first observation of the new episode   */
-    int32_t fk_mode;               /* 0 auto, 1 generic DH chain, 2 closed-form (ref arm) */
+    int32_t fk_mode;               /* 0 auto (closed form / preset / NVRTC-specialised / run-time
+                                      table, in that order), 1 run-time DH table, 2 closed form
+                                      required, 3 NVRTC specialisation required              */
     int32_t action_low;            /* action_sample range [low, high) (-180, 180, :216)   */
     int32_t action_high;
     uint64_t seed;                 /* Philox key for on-device actions / objectives       */

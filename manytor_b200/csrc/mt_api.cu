@@ -10,6 +10,7 @@
 #include <new>
 #include <unordered_map>
 
+#include "mt_jit.cuh"
 #include "mt_step.cuh"
 
 using namespace mt;
@@ -54,7 +55,13 @@ struct DeviceGuard {
 struct mt_env {
     mt_config cfg;
     long long n, n_pad, n_tiles;
-    int arm;  // 0 = closed form reference arm, else J (generic chain)
+    int arm;  // 0 = closed form reference arm, 2..8 = J (run-time DH table), >= 100 = preset arm
+    // NVRTC-specialised step kernels for this handle's own DH table (mt_jit.cuh); the helper kernels
+    // keep using the run-time table (`arm`)
+    bool jit = false;
+    int jit_id = 0, jit_x = 0;
+    std::string jit_preset;
+    cudaKernel_t jit_kernel[2][2] = {};
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;
@@ -109,7 +116,10 @@ static bool is_preset_arm(const mt_config &c) {
     return c.obs_frame == J - 1 && c.ground_frame_a == J - 1 && c.ground_frame_b == J && c.catch_frame == J;
 }
 
-static double snap(double v) { return std::fabs(v) < 1e-12 ? 0.0 : (std::fabs(std::fabs(v) - 1.0) < 1e-12 ? (v > 0 ? 1.0 : -1.0) : v); }
+// cos/sin of the table's alpha and theta offsets: the table arrives as fp32 (pi/2 -> 1.57079637, whose
+// cosine is -4.4e-8, where the reference's fp64 np.pi/2 gives 6e-17), so values within fp32 rounding of
+// 0 or +-1 are snapped; this is also what lets the specialised kernels fold them away.
+static double snap(double v) { return std::fabs(v) < 5e-7 ? 0.0 : (std::fabs(std::fabs(v) - 1.0) < 5e-7 ? (v > 0 ? 1.0 : -1.0) : v); }
 
 extern "C" int mt_abi_version(void) { return MT_ABI_VERSION; }
 extern "C" const char *mt_last_error(void) { return g_err; }
@@ -154,7 +164,7 @@ static int validate(const mt_config &c) {
     if (c.horizon < 0 || c.horizon > 65535) return fail(MT_ERR_INVALID, "horizon must be in [0, 65535]");
     if (c.action_high <= c.action_low) return fail(MT_ERR_INVALID, "action_high must exceed action_low");
     if (!(c.radius > 0.f) || !(c.catch_tol >= 0.f)) return fail(MT_ERR_INVALID, "radius must be > 0 and catch_tol >= 0");
-    if (c.fk_mode < 0 || c.fk_mode > 2) return fail(MT_ERR_INVALID, "fk_mode must be 0, 1 or 2");
+    if (c.fk_mode < 0 || c.fk_mode > 3) return fail(MT_ERR_INVALID, "fk_mode must be 0, 1, 2 or 3");
     if (c.fk_mode == 2 && !is_reference_arm(c)) return fail(MT_ERR_INVALID, "fk_mode=2 (closed form) needs the reference DH table and frames");
     return MT_OK;
 }
@@ -272,6 +282,32 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.tile_begin = 0;
     e->base.tile_end = e->n_tiles;
     e->base.pair_layout = has_specialised_x(e->arm, cfg->n_obj) ? 1 : 0;
+    // any other table with the usual frame selectors: specialise the step kernel for it at run time
+    const int nj = cfg->n_joints;
+    const bool usual = cfg->obs_frame == nj - 1 && cfg->ground_frame_a == nj - 1 && cfg->ground_frame_b == nj && cfg->catch_frame == nj;
+    const char *off = std::getenv("MT_DISABLE_JIT");
+    const bool want_jit = cfg->fk_mode == 3 || (cfg->fk_mode == 0 && e->arm >= 2 && e->arm <= MT_MAX_JOINTS && !(off && off[0] == '1'));
+    if (want_jit) {
+        std::string err;
+        if (!usual) {
+            err = "run-time specialisation needs the usual frame selectors (obs J-1, ground J-1 and J, catch J)";
+        } else {
+            e->jit_id = 1000 + nj;
+            e->jit_x = (cfg->n_obj % 2 == 0) ? cfg->n_obj : 0;       // even X: packed pair layout
+            e->jit_preset = preset_source(e->jit_id, nj, e->base.arm);
+            JitKernel k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, false, true, err);
+            if (k.kernel) {
+                e->jit = true;
+                e->jit_kernel[0][1] = k.kernel;
+                e->base.pair_layout = e->jit_x != 0 ? 1 : 0;
+            }
+        }
+        if (!e->jit && cfg->fk_mode == 3) {
+            int rc = fail(MT_ERR_INVALID, "fk_mode=3 (run-time specialisation) unavailable: %s", err.c_str());
+            mt_destroy(e);
+            return rc;
+        }
+    }
     *out = e;
     return MT_OK;
 }
@@ -555,19 +591,31 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     P.step_hi = (uint32_t)(e->step_index >> 32);
     P.tile_begin = t0;
     P.tile_end = t1;
-    StepFn fn = pick_kernel(e->arm, e->cfg.n_obj, rnd, obs != nullptr);
+    const bool wobs = obs != nullptr;
+    const void *fn = nullptr;
+    if (e->jit) {
+        cudaKernel_t &k = e->jit_kernel[rnd ? 1 : 0][wobs ? 1 : 0];
+        if (!k) {                                             // other variants compile on first use
+            std::string err;
+            k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, rnd, wobs, err).kernel;
+            if (!k) return fail(MT_ERR_CUDA, "run-time specialisation failed: %s", err.c_str());
+        }
+        fn = (const void *)k;
+    } else {
+        fn = (const void *)pick_kernel(e->arm, e->cfg.n_obj, rnd, wobs);
+    }
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
     const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
     const size_t smem = nb * kWarpsPerBlock * P.tile_bytes + nb * kWarpsPerBlock * sizeof(uint64_t);
     int per_sm = 0;
-    auto hit = e->blocks_per_sm.find((const void *)fn);
+    auto hit = e->blocks_per_sm.find(fn);
     if (hit != e->blocks_per_sm.end()) {
         per_sm = hit->second;
     } else {
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)fn, kWarpsPerBlock * kTile, smem));
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * kTile, smem));
         if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
-        e->blocks_per_sm[(const void *)fn] = per_sm;
+        e->blocks_per_sm[fn] = per_sm;
     }
     const long long tiles = t1 - t0;
     const long long want = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
@@ -584,7 +632,8 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = attr;
     lc.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&lc, fn, P));
+    void *args[] = {(void *)&P};
+    CU(cudaLaunchKernelExC(&lc, fn, args));
     e->launches++;
     return MT_OK;
 }

@@ -4,9 +4,12 @@ Device time with CUDA events, 1 s clock warm-up, median of 5 rounds of 300 steps
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from manytor_b200 import BatchedEnvs, UR5_ARM, REFERENCE_ARM
+from manytor_b200 import ArmSpec, BatchedEnvs, UR5_ARM, REFERENCE_ARM
 
 PEAK = 6453.1
+# UR5 with other link lengths: not a built-in preset, so it goes through the NVRTC path
+CUSTOM6 = ArmSpec(dh=tuple((r[0] * 1.1, r[1], r[2] * 0.9, r[3]) for r in UR5_ARM.dh), obs_frame=5, ground_frames=(5, 6),
+                  catch_frame=6, radius=0.85, catch_tol=0.13)
 try:
     PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
@@ -47,6 +50,8 @@ CASES = [("config2: 4096 envs, J=4, x=10 (in L2)", 4096, 10, REFERENCE_ARM, {}),
          ("config3: 2^20 envs, J=4, x=10", 1 << 20, 10, REFERENCE_ARM, {}),
          ("config3 via generic DH chain (fk_mode=1)", 1 << 20, 10, REFERENCE_ARM, dict(fk_mode=1)),
          ("config5: 2^20 envs, J=6 UR5, x=20", 1 << 20, 20, UR5_ARM, {}),
+         ("config5 run-time table (fk_mode=1)", 1 << 20, 20, UR5_ARM, dict(fk_mode=1)),
+         ("6-DOF custom table, x=20, NVRTC-specialised", 1 << 20, 20, CUSTOM6, dict(fk_mode=3)),
          ("2^22 envs, J=4, x=10", 1 << 22, 10, REFERENCE_ARM, dict(K=100))]
 only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, n, x, arm, kw in CASES:
