@@ -184,3 +184,40 @@ def test_plain_c_host_runs(tor, tmp_path):
     res = subprocess.run([exe, "5000", "60"], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr + res.stdout
     assert "envs 5000 steps 60" in res.stdout and "300000 env-steps" in res.stdout
+
+
+@pytest.mark.parametrize("n,x", [(1, 10), (31, 10), (33, 7), (95, 20), (1000, 10), (4097, 10)])
+def test_outputs_stay_inside_their_buffers(tor, n, x):
+    """compute-sanitizer is closed on this pool, so overruns of the caller's output buffers (the tail
+    tile is the risky one: its observations may not leave by a whole-tile bulk store) are caught with
+    guard bands: every output lives inside a larger sentinel-filled allocation."""
+    import ctypes as C
+    import torch
+    from manytor_b200 import BatchedEnvs, _lib
+    env = BatchedEnvs(n, x, device=0, auto_reset=True, horizon=4, obs_after_reset=True, seed=n)
+    env.reset()
+    lib = _lib.load()
+    G = 4096                                                  # guard elements on each side (16-byte multiples)
+    SENT = -12345.0
+
+    def guarded(count, dtype, fill):
+        t = torch.full((count + 2 * G,), fill, dtype=dtype, device="cuda")
+        return t, t[G:G + count]
+
+    obs_all, obs = guarded(n * 3 * x, torch.float32, SENT)
+    rew_all, rew = guarded(n, torch.float32, SENT)
+    done_all, done = guarded(n, torch.uint8, 77)
+    jn_all, jn = guarded(n * 4 * 3, torch.float32, SENT)
+    act_all, act = guarded(n * 4, torch.float32, 0.0)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    for it in range(6):
+        _lib.check(lib.mt_sample_actions(env._h, p(act), stream))
+        _lib.check(lib.mt_step(env._h, p(act), p(obs), p(rew), p(done), p(jn), stream))
+        _lib.check(lib.mt_rollout_random(env._h, 1, p(obs), p(rew), p(done), stream))
+        _lib.check(lib.mt_observe(env._h, p(obs), stream))
+    torch.cuda.synchronize()
+    for whole, fill in ((obs_all, SENT), (rew_all, SENT), (jn_all, SENT), (act_all, 0.0)):
+        assert bool((whole[:G] == fill).all()) and bool((whole[-G:] == fill).all())
+    assert bool((done_all[:G] == 77).all()) and bool((done_all[-G:] == 77).all())
+    assert bool((obs != SENT).all()) and bool((rew != SENT).all()) and bool((done <= 2).all()) and bool((jn != SENT).all())
