@@ -28,16 +28,6 @@ __device__ __forceinline__ void sincos_deg(float x, float &s, float &c) {
     c = ((q + 1) & 2) ? -cc : cc;
 }
 
-// sin/cos of a SMALL angle in degrees, |x| <= 45: quadrant 0 of the reduction
-// above, so no rint / swap / sign logic (used for the per-sub-pose half steps).
-__device__ __forceinline__ void sincos_deg_small(float x, float &s, float &c) {
-    const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f;
-    float r = fmaf(x, inv_lo, x * inv_hi);
-    float u = r * r;
-    s = fmaf(fmaf(fmaf(-0.58907866f, u, 2.5497673f), u, -5.1677079f), u, 3.14159274f) * r;
-    c = fmaf(fmaf(fmaf(fmaf(0.23132971f, u, -1.33504462f), u, 4.05870724f), u, -4.93480206f), u, 1.0f);
-}
-
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

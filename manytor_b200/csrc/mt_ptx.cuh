@@ -39,20 +39,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-// HBM -> shared, completion counted in bytes on `bar`.  16-byte aligned, size % 16 == 0.
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_addr(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
-                 : "memory");
-}
-
-// shared -> HBM as part of the thread's current bulk group
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"(smem_addr(src_smem)), "r"(bytes)
-                 : "memory");
-}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the sources of all committed bulk stores have been read (smem reusable)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -111,6 +97,7 @@ __device__ __forceinline__ void st_hint(uint32_t *a, uint32_t v, uint64_t pol) {
 __device__ __forceinline__ void st_hint(uint8_t *a, uint8_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"((uint32_t)v), "l"(pol) : "memory");
 }
+// HBM -> shared, completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0; `pol` = L2 eviction policy
 __device__ __forceinline__ void bulk_load_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
                                                uint64_t pol) {
     asm volatile(
@@ -119,6 +106,7 @@ __device__ __forceinline__ void bulk_load_hint(void *dst_smem, const void *src_g
         "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
         : "memory");
 }
+// shared -> HBM as part of the thread's current bulk group
 __device__ __forceinline__ void bulk_store_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
                  "r"(smem_addr(src_smem)), "r"(bytes), "l"(pol)

@@ -81,13 +81,6 @@ struct Frames {
     float zmin;        // min z of the two ground frames over all sub-poses (manytor.py:191)
 };
 
-// rotate (c, s) by minus delta: angle <- angle - d
-__device__ __forceinline__ void rot_back(float &c, float &s, float cd, float sd) {
-    float nc = fmaf(c, cd, s * sd);
-    s = fmaf(s, cd, -(c * sd));
-    c = nc;
-}
-
 // Reference arm, closed form: with alpha = -+pi/2 the chain of
 // manytor.py:42-52 collapses to
 //   frame2 = (0, 0, 4.3)
