@@ -97,9 +97,6 @@ static bool is_reference_arm(const mt_config &c) {
     return c.obs_frame == 3 && c.ground_frame_a == 3 && c.ground_frame_b == 4 && c.catch_frame == 4;
 }
 
-// X values with a specialised (compile-time, packed pair layout) kernel -- keep in sync with pick_kernel
-static bool has_specialised_x(int arm, int x) { return (arm == 0 || arm == 6 || arm >= 100) && (x == 10 || x == 20); }
-
 // does the configuration describe the preset arm `id` (table within 1e-6, usual frame selectors)?
 template <int ID>
 static bool is_preset_arm(const mt_config &c) {
@@ -281,28 +278,31 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.n = e->n;
     e->base.tile_begin = 0;
     e->base.tile_end = e->n_tiles;
-    e->base.pair_layout = has_specialised_x(e->arm, cfg->n_obj) ? 1 : 0;
-    // any other table with the usual frame selectors: specialise the step kernel for it at run time
+    e->base.pair_layout = (cfg->n_obj % 2 == 0) ? 1 : 0;      // even X: pair-interleaved objectives (mt_step.cuh)
+    // Run-time specialisation (mt_jit.cuh): a run-time table with the usual frame selectors gets its own
+    // Preset<>; a built-in arm with an objective count other than the pre-compiled 10 / 20 gets the same arm
+    // code with X as a compile-time constant (unrolled objective walk).
     const int nj = cfg->n_joints;
     const bool usual = cfg->obs_frame == nj - 1 && cfg->ground_frame_a == nj - 1 && cfg->ground_frame_b == nj && cfg->catch_frame == nj;
     const char *off = std::getenv("MT_DISABLE_JIT");
-    const bool want_jit = cfg->fk_mode == 3 || (cfg->fk_mode == 0 && e->arm >= 2 && e->arm <= MT_MAX_JOINTS && !(off && off[0] == '1'));
-    if (want_jit) {
+    const bool allowed = cfg->fk_mode == 3 || (cfg->fk_mode == 0 && !(off && off[0] == '1'));
+    const bool runtime_table = e->arm >= 2 && e->arm <= MT_MAX_JOINTS;
+    const bool other_x = !runtime_table && cfg->n_obj != 10 && cfg->n_obj != 20;
+    if (allowed && (runtime_table || other_x)) {
         std::string err;
-        if (!usual) {
+        if (runtime_table && !usual) {
             err = "run-time specialisation needs the usual frame selectors (obs J-1, ground J-1 and J, catch J)";
         } else {
-            e->jit_id = 1000 + nj;
-            e->jit_x = (cfg->n_obj % 2 == 0) ? cfg->n_obj : 0;       // even X: packed pair layout
-            e->jit_preset = preset_source(e->jit_id, nj, e->base.arm);
+            e->jit_id = runtime_table ? 1000 + nj : e->arm;
+            e->jit_x = cfg->n_obj;                                    // compile-time X: unrolled objective walk
+            e->jit_preset = runtime_table ? preset_source(e->jit_id, nj, e->base.arm) : std::string();
             JitKernel k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, false, true, err);
             if (k.kernel) {
                 e->jit = true;
                 e->jit_kernel[0][1] = k.kernel;
-                e->base.pair_layout = e->jit_x != 0 ? 1 : 0;
             }
         }
-        if (!e->jit && cfg->fk_mode == 3) {
+        if (!e->jit && cfg->fk_mode == 3 && runtime_table) {
             int rc = fail(MT_ERR_INVALID, "fk_mode=3 (run-time specialisation) unavailable: %s", err.c_str());
             mt_destroy(e);
             return rc;

@@ -410,45 +410,16 @@ __device__ __forceinline__ bool one_objective(float &px, float &py, float &pz, c
 }
 
 // Layout of one env's objectives inside its row of 3X floats.
-//   pair layout (X even, the specialised kernels): objectives are stored two by two,
+//   pair layout (every EVEN X): objectives are stored two by two,
 //   component-interleaved -- [x0 x1 | y0 y1 | z0 z1] per pair -- so one 64-bit shared-memory load
 //   yields the packed operand (x0, x1) for the FADD2/FFMA2 pipeline; observations are written back
 //   in place in the public row-major order [d0 r0 t0 d1 r1 t1], which spans the same 6 floats.
-//   plain layout (run-time X): row-major [x y z] per objective.
+//   plain layout (every ODD X): row-major [x y z] per objective.
 // Either way a lane only ever touches its own row, and the row stride (3X words) keeps 64/128-bit
 // accesses of consecutive lanes on distinct banks for X = 10 / 20.
-template <int X> struct PairLayout { static constexpr bool value = (X != 0) && (X % 2 == 0); };
 
 __host__ __device__ __forceinline__ int point_index(bool pair_layout, int pt, int comp) {
     return pair_layout ? (pt >> 1) * 6 + comp * 2 + (pt & 1) : pt * 3 + comp;
-}
-
-// Vector width for the plain in-place row walk: the widest power of two (<= 4 floats) dividing
-// the row length 3X, which keeps the per-lane row stride odd in vector units (no bank conflicts).
-template <int X> struct RowVec { static constexpr int value = (X % 4 == 0) ? 4 : ((X % 2 == 0) ? 2 : 1); };
-template <> struct RowVec<0> { static constexpr int value = 1; };
-
-template <int V> struct VecT;
-template <> struct VecT<1> { using type = float; };
-template <> struct VecT<2> { using type = float2; };
-template <> struct VecT<4> { using type = float4; };
-
-template <int V>
-__device__ __forceinline__ void vload(const float *p, float *v) {
-    using T = typename VecT<V>::type;
-    T t = *reinterpret_cast<const T *>(p);
-    const float *q = reinterpret_cast<const float *>(&t);
-#pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = q[i];
-}
-template <int V>
-__device__ __forceinline__ void vstore(float *p, const float *v) {
-    using T = typename VecT<V>::type;
-    T t;
-    float *q = reinterpret_cast<float *>(&t);
-#pragma unroll
-    for (int i = 0; i < V; ++i) q[i] = v[i];
-    *reinterpret_cast<T *>(p) = t;
 }
 
 // Two objectives at once, packed (manytor.py:141-153, 17-22, 158-168).  In: (x0,x1), (y0,y1),
@@ -483,9 +454,11 @@ __device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 
 template <int X, bool WOBS>
 __device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f, float tol, uint32_t alive) {
     uint32_t caught = 0;
-    if (PairLayout<X>::value) {
+    const int xx = X ? X : x;
+    if ((xx & 1) == 0) {
+        // even X: pair-interleaved layout, one 64-bit access per packed operand
 #pragma unroll
-        for (int pr = 0; pr < X / 2; ++pr) {
+        for (int pr = 0; pr < (X ? X / 2 : xx >> 1); ++pr) {
             float *q = row + pr * 6;
             const float2 PX = *reinterpret_cast<const float2 *>(q);
             const float2 PY = *reinterpret_cast<const float2 *>(q + 2);
@@ -501,24 +474,26 @@ __device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f,
             }
         }
     } else {
-        constexpr int V = RowVec<X>::value;
-        const int iters = (X ? X : x) / V;
+        // odd X: plain row-major layout (the row stride 3X is odd, so 32-bit accesses of consecutive lanes
+        // fall on distinct banks); still two objectives per packed evaluation, plus one left over
+        int pt = 0;
 #pragma unroll
-        for (int it = 0; it < iters; ++it) {
-            float v[3 * V];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) vload<V>(row + (it * 3 + i) * V, v + i * V);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const int pt = it * V + j;
-                bool c = one_objective<WOBS>(v[3 * j], v[3 * j + 1], v[3 * j + 2], f, tol, (alive >> pt) & 1u);
-                caught |= c ? (1u << pt) : 0u;
-            }
+        for (; pt + 1 < xx; pt += 2) {
+            float *q = row + pt * 3;
+            const float2 PX = make_float2(q[0], q[3]), PY = make_float2(q[1], q[4]), PZ = make_float2(q[2], q[5]);
+            float o[6];
+            const uint32_t c = pair_objective<WOBS>(PX, PY, PZ, f, tol, (alive >> pt) & 1u, (alive >> (pt + 1)) & 1u, o);
+            caught |= c << pt;
             if (WOBS) {
 #pragma unroll
-                for (int i = 0; i < 3; ++i) vstore<V>(row + (it * 3 + i) * V, v + i * V);
+                for (int k = 0; k < 6; ++k) q[k] = o[k];
             }
         }
+        float *q = row + pt * 3;
+        float px = q[0], py = q[1], pz = q[2];
+        const bool c = one_objective<WOBS>(px, py, pz, f, tol, (alive >> pt) & 1u);
+        caught |= c ? (1u << pt) : 0u;
+        if (WOBS) { q[0] = px; q[1] = py; q[2] = pz; }
     }
     return caught;
 }
@@ -739,9 +714,9 @@ step_kernel(const __grid_constant__ StepParams P) {
                     sample_point(P, P.env_id_base + renv, ep, lane, px, py, pz);
                 }
                 float *grow = P.points + renv * rowlen;
-                grow[point_index(PairLayout<X>::value, lane, 0)] = px;
-                grow[point_index(PairLayout<X>::value, lane, 1)] = py;
-                grow[point_index(PairLayout<X>::value, lane, 2)] = pz;
+                grow[point_index((x & 1) == 0, lane, 0)] = px;
+                grow[point_index((x & 1) == 0, lane, 1)] = py;
+                grow[point_index((x & 1) == 0, lane, 2)] = pz;
                 if (WOBS && (P.flags & kObsAfterReset)) {
                     Frames f0;
                     f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
