@@ -9,14 +9,14 @@
 //   is_done       manytor.py:155-173
 //   reset         manytor.py:219-241   (auto-reset with on-device objective refresh)
 //
-// Mapping: one warp owns a tile of 32 consecutive envs, one lane per env.  The
-// tile's objectives ([32][X][3] fp32, 120 B per env at X=10) are fetched from HBM
-// by ONE TMA bulk copy into shared memory while the lanes do the kinematics
-// (which need no objectives); observations are written in place over the
-// objectives and leave by ONE TMA bulk store, so the row-major [N][3X] layouts
-// are moved with full-line transactions and no per-lane strided access.  All
-// other state is fp32/u32 structure-of-arrays read and written once per step
-// with coalesced (vector) accesses.
+// Mapping: persistent warps; one warp owns a tile of 32 consecutive envs at a time, one lane per
+// env.  The tile's objectives (3X fp32 per env, 120 B at X=10) are fetched from HBM by ONE TMA bulk
+// copy into shared memory while the lanes do the kinematics (which need no objectives);
+// observations are written in place over the objectives and leave by ONE TMA bulk store, so the
+// row-major [N][3X] layouts are moved with full-line transactions and no per-lane strided access.
+// All other state is fp32/u32 structure-of-arrays, read and written once per step with coalesced
+// (vector) accesses and prefetched one tile ahead.  Independent fp32 work is packed two lanes per
+// instruction (FFMA2 / FADD2 / FMUL2).  DESIGN.md section 4 has the measurements behind each choice.
 #pragma once
 #include "../../include/manytor_b200.h"
 #include "mt_math.cuh"
@@ -96,9 +96,10 @@ struct Frames {
 // uB are four sampled cosines.  Each is advanced by Reinsch's recurrence
 //   x <- x + d;  d <- d - 4 sin^2(delta/2) x
 // (2 FMA-class ops per value per sub-pose, error growth linear in the step
-// count), run backwards from the exact final pose: 13 instructions per sub-pose
-// instead of 3 plane rotations + products.  tools/emulate_subpose.py compares it
-// with fp64: max |dz| 3.5e-5 over 4e5 random steps, no ground-flag flips.
+// count), run backwards from the exact final pose: 9 instructions per sub-pose
+// instead of 3 plane rotations + products (26).  tools/emulate_subpose.py compares
+// it with fp64: max |dz| 3.5e-5 over 4e5 random steps, no ground-flag flips.
+
 // Two cosine sequences advanced together (one FADD2 + one FFMA2 per sub-pose).
 struct CosSeq2 {
     float2 x, d, na;  // values, backward differences, -4 sin^2(delta/2)
