@@ -221,3 +221,34 @@ def test_outputs_stay_inside_their_buffers(tor, n, x):
         assert bool((whole[:G] == fill).all()) and bool((whole[-G:] == fill).all())
     assert bool((done_all[:G] == 77).all()) and bool((done_all[-G:] == 77).all())
     assert bool((obs != SENT).all()) and bool((rew != SENT).all()) and bool((done <= 2).all()) and bool((jn != SENT).all())
+
+
+def test_remaining_entry_points(tor):
+    """step_host without observations, stats clear, config read-back, seeds."""
+    import ctypes as C
+    import torch
+    from manytor_b200 import BatchedEnvs, _lib
+    n = 3000
+    a = BatchedEnvs(n, 10, device=0, seed=1, auto_reset=True, horizon=5)
+    b = BatchedEnvs(n, 10, device=0, seed=1, auto_reset=True, horizon=5)
+    a.reset(); b.reset()
+    rng = np.random.RandomState(0)
+    for _ in range(7):
+        act = rng.randint(-180, 180, size=(n, 4)).astype(np.float32)
+        oa, ra, da = a.step_host(act, write_obs=False)
+        ob, rb, db = b.step_host(act)
+        assert oa is None
+        np.testing.assert_array_equal(ra, rb)
+        np.testing.assert_array_equal(da, db)
+    assert a.stats() == b.stats() and a.stats()["episodes"] >= n
+    a.clear_stats()
+    s = a.stats()
+    assert s["episodes"] == 0 and s["env_steps"] == 0 and s["reward_sum"] == 0
+    cfg = _lib.MtConfig()
+    _lib.check(_lib.load().mt_get_config(a._h, C.byref(cfg)))
+    assert (cfg.n_envs, cfg.n_obj, cfg.horizon, cfg.auto_reset, cfg.seed) == (n, 10, 5, 1, 1)
+    # re-seeding changes the action stream from the next launch on
+    x0 = a.sample_actions().clone()
+    a.set_seed(2)
+    x1 = a.sample_actions()
+    assert not torch.equal(x0, x1)
