@@ -209,6 +209,7 @@ def run_gpu(args) -> None:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     manytor_b200.load_library()
+    cores = mtd.bind_to_gpu_numa(local) if world > 1 else None      # keep pinned buffers on the GPU's NUMA node
 
     n = ENVS_PER_GPU
     base, _ = rank * n, n
@@ -376,7 +377,8 @@ def run_gpu(args) -> None:
                          "envs_per_launch": n},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers, 16 chunks over 4 streams)"},
+                    "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers, 16 chunks over 4 streams)",
+                    "cpu_binding": f"{len(cores)} cores next to the GPU (NVML affinity)" if cores else "none"},
             "gpu_launches": launches,
             "clocks": clocks,
             "modes": modes,

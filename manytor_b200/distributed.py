@@ -42,6 +42,26 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def bind_to_gpu_numa(local_rank: int) -> Optional[list]:
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity) so that pinned host
+    buffers and the H2D/D2H copies of the host-buffer step stay on the GPU's NUMA node.  Returns the
+    cores, or None when NVML / affinity control is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """Sum the per-shard statistics vector over all ranks (in place) -- the single
     collective of a multi-GPU rollout."""
