@@ -69,7 +69,9 @@ typedef struct mt_config {
     float catch_tol;               /* per-axis inclusive tolerance (8.0, :162)            */
     int32_t substeps;              /* interpolated poses per step (25, :178)              */
     int32_t horizon;               /* max steps per episode, 0 = none (max_steps in the
-                                      reference's driver scripts, test_single.py:6)       */
+                                      reference's driver scripts, test_single.py:6), at most
+                                      65535; the per-env episode-length and ground-contact
+                                      counters are 16-bit and saturate there when horizon = 0 */
     int32_t terminate_on_ground;   /* 0 = reference code (reward -1 only), 1 = README     */
     int32_t auto_reset;            /* 1: envs that end are reset inside the step kernel   */
     int32_t obs_after_reset;       /* with auto_reset: 0 = emit obs2 of the ending step,
