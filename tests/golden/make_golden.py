@@ -132,6 +132,9 @@ def main():
         "batch32_x10_seed2": dict(seed=2, n_envs=32, x=10, steps=150, reset_on_done=True),
         # few objectives -> frequent all-collected terminations and resets
         "batch16_x2_seed3": dict(seed=3, n_envs=16, x=2, steps=150, reset_on_done=True),
+        # Multienv's own defaults: env_shape=(1, 2), obj_number=5 (manytor.py:77)
+        "multi_default_1x2_x5_seed5": dict(seed=5, n_envs=2, x=5, steps=120, reset_on_done=False,
+                                           use_multienv=(1, 2), epochs=2),
         # x=10 run long enough (mean episode ~550 steps) to see all-collected + refresh
         "batch8_x10_seed4": dict(seed=4, n_envs=8, x=10, steps=900, reset_on_done=True),
     }

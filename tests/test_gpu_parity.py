@@ -11,7 +11,7 @@ from parity import Report, alive_bits_to_matrix, compare_step, lockstep
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["single_x10_seed0", "multi_3x2_x7_seed1", "batch32_x10_seed2", "batch16_x2_seed3", "batch8_x10_seed4"]
+GOLDEN = ["single_x10_seed0", "multi_3x2_x7_seed1", "batch32_x10_seed2", "batch16_x2_seed3", "batch8_x10_seed4", "multi_default_1x2_x5_seed5"]
 
 
 @pytest.fixture(scope="module")
