@@ -70,8 +70,10 @@ typedef struct mt_config {
     int32_t substeps;              /* interpolated poses per step (25, :178)              */
     int32_t horizon;               /* max steps per episode, 0 = none (max_steps in the
                                       reference's driver scripts, test_single.py:6), at most
-                                      65535; the per-env episode-length and ground-contact
-                                      counters are 16-bit and saturate there when horizon = 0 */
+                                      65535.  The per-env episode-length counter saturates: at
+                                      65535 when n_obj <= 16 or horizon = 0, else at
+                                      2^(32 - n_obj) - 1 when the horizon fits below that (the
+                                      counter then shares a word with the alive mask), else 65535 */
     int32_t terminate_on_ground;   /* 0 = reference code (reward -1 only), 1 = README     */
     int32_t auto_reset;            /* 1: envs that end are reset inside the step kernel   */
     int32_t obs_after_reset;       /* with auto_reset: 0 = emit obs2 of the ending step,
@@ -93,7 +95,7 @@ typedef struct mt_stats {
     int64_t reward_sum;      /* sum of total_reward over finished episodes               */
     int64_t length_sum;      /* sum of episode lengths over finished episodes            */
     int64_t catches;         /* objectives collected in finished episodes                */
-    int64_t ground_steps;    /* steps with ground contact in finished episodes           */
+    int64_t ground_steps;    /* env-steps with ground contact (every executed step)      */
     int64_t live_reward_sum; /* sum of total_reward over episodes still in progress      */
 } mt_stats;
 #define MT_STATS_WORDS 8

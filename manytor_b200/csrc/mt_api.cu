@@ -65,6 +65,8 @@ struct mt_env {
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;
+    int32_t ep_shift = 0;      // > 0: ep_len packed into the alive word above bit ep_shift
+    uint32_t ep_max = 65535u;
     int num_sms = 0;
     std::unordered_map<const void *, int> blocks_per_sm;   // occupancy of each step-kernel variant, queried once
     const float *obj_stream = nullptr;
@@ -146,6 +148,12 @@ extern "C" int mt_config_init(mt_config *cfg) {
     cfg->action_high = 180;
     cfg->seed = 0;
     return MT_OK;
+}
+
+__global__ void policy_kernel(unsigned long long *out) {
+    out[0] = policy_evict_last();
+    out[1] = policy_evict_normal();
+    out[2] = policy_evict_first();
 }
 
 static int validate(const mt_config &c) {
@@ -261,10 +269,18 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     ALLOC(e->goals, np * J * 4);
     ALLOC(e->alive, np * 4);
     ALLOC(e->total_reward, np * 4);
-    ALLOC(e->counters, np * 4);
+    // episode length: in the spare bits of the alive word when they can hold it (mt_step.cuh, StepParams::ep_shift)
+    {
+        const int shift = cfg->n_obj <= 16 ? 16 : cfg->n_obj;
+        const bool packed = cfg->n_obj <= 16 || (cfg->n_obj < 32 && cfg->horizon > 0 && cfg->horizon < (1 << (32 - shift)));
+        e->ep_shift = packed ? shift : 0;
+        e->ep_max = packed ? (uint32_t)((1ull << (32 - shift)) - 1ull) : 65535u;
+        if (e->ep_max > 65535u) e->ep_max = 65535u;
+    }
+    if (!e->ep_shift) ALLOC(e->counters, np * 4);
     ALLOC(e->episode, np * 4);
     ALLOC(e->points, np * X * 3 * 4);
-    ALLOC(e->stats, MT_STATS_WORDS * 8);
+    ALLOC(e->stats, (MT_STATS_WORDS + kGroundSlots) * 8);
 #undef ALLOC
     e->num_sms = prop.multiProcessorCount;
     fill_params(*cfg, e->base);
@@ -279,6 +295,27 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.tile_begin = 0;
     e->base.tile_end = e->n_tiles;
     e->base.pair_layout = (cfg->n_obj % 2 == 0) ? 1 : 0;      // even X: pair-interleaved objectives (mt_step.cuh)
+    e->base.ep_shift = e->ep_shift;
+    e->base.ep_max = e->ep_max;
+    {
+        policy_kernel<<<1, 1>>>(e->stats);                       // stats words are zeroed again right below
+        unsigned long long pol[3] = {0, 0, 0};
+        cudaError_t pe = cudaMemcpy(pol, e->stats, sizeof(pol), cudaMemcpyDeviceToHost);
+        if (pe == cudaSuccess) pe = cudaMemset(e->stats, 0, sizeof(pol));
+        if (pe != cudaSuccess) {
+            int rc = fail(MT_ERR_CUDA, "L2 policy setup failed: %s", cudaGetErrorString(pe));
+            mt_destroy(e);
+            return rc;
+        }
+        e->base.pol_last = pol[0]; e->base.pol_normal = pol[1]; e->base.pol_stream = pol[2];
+    }
+    {
+        // evict_last budget for the per-env state: 36 MB of the 126 MB L2 (MT_L2_KEEP_MB overrides, 0 = none)
+        double keep_mb = 36.0;
+        if (const char *kb = std::getenv("MT_L2_KEEP_MB")) keep_mb = std::atof(kb);
+        const double state_bytes = 4.0 * J + 8.0 + (e->ep_shift ? 0.0 : 4.0);
+        e->base.keep_tiles = (long long)(keep_mb * 1048576.0 / state_bytes) / kTile;
+    }
     // Run-time specialisation (mt_jit.cuh): a run-time table with the usual frame selectors gets its own
     // Preset<>; a built-in arm with an objective count other than the pre-compiled 10 / 20 gets the same arm
     // code with X as a compile-time constant (unrolled objective walk).
@@ -376,8 +413,8 @@ __global__ void reset_kernel(const __grid_constant__ StepParams P, const uint8_t
     }
     for (int i = 0; i < J; ++i) P.goals[env * J + i] = 0.f;           // manytor.py:220
     P.total_reward[env] = 0.f;                                        // manytor.py:221
-    P.alive[env] = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);        // manytor.py:222
-    P.counters[env] = 0u;
+    P.alive[env] = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);        // manytor.py:222 (and ep_len = 0 when packed)
+    if (!P.ep_shift) P.counters[env] = 0u;
 }
 
 __global__ void observe_kernel(const __grid_constant__ StepParams P, int arm, float *obs) {
@@ -388,7 +425,7 @@ __global__ void observe_kernel(const __grid_constant__ StepParams P, int arm, fl
     for (int i = 0; i < J; ++i) g[i] = P.goals[env * J + i];
     Frames f;
     pose_of(P, arm, g, f, nullptr);
-    const uint32_t alive = P.alive[env];
+    const uint32_t alive = alive_mask_of(P, P.alive[env]);
     const float *row = P.points + env * 3 * x;
     float *dst = obs + env * 3 * x;
     for (int pt = 0; pt < x; ++pt) {
@@ -426,7 +463,7 @@ __global__ void get_points_kernel(const __grid_constant__ StepParams P, float *d
     if (i >= P.n * row) return;
     const long long env = i / row;
     const int k = (int)(i - env * row), pt = k / 3;
-    const bool dead = zero_dead && !((P.alive[env] >> pt) & 1u);      // manytor.py:148
+    const bool dead = zero_dead && !((alive_mask_of(P, P.alive[env]) >> pt) & 1u);   // manytor.py:148
     dst[i] = dead ? 0.f : P.points[env * row + point_index(P.pair_layout, pt, k % 3)];
 }
 
@@ -437,9 +474,18 @@ __global__ void set_state_kernel(const __grid_constant__ StepParams P, const flo
     if (mask && !mask[env]) return;
     const int J = P.n_joints;
     if (goals) for (int i = 0; i < J; ++i) P.goals[env * J + i] = goals[env * J + i];
-    if (alive) P.alive[env] = alive[env];
+    const uint32_t len = eplen ? (uint32_t)min(max(eplen[env], 0), (int)P.ep_max) : 0u;
+    if (P.ep_shift) {
+        const uint32_t amask = (1u << P.ep_shift) - 1u;
+        uint32_t w = P.alive[env];
+        if (alive) w = (w & ~amask) | (alive[env] & amask);
+        if (eplen) w = (w & amask) | (len << P.ep_shift);
+        P.alive[env] = w;
+    } else {
+        if (alive) P.alive[env] = alive[env];
+        if (eplen) P.counters[env] = len;
+    }
     if (total) P.total_reward[env] = total[env];
-    if (eplen) P.counters[env] = (P.counters[env] & 0xffff0000u) | (uint32_t)min(max(eplen[env], 0), 65535);
 }
 
 __global__ void get_state_kernel(const __grid_constant__ StepParams P, float *goals, uint32_t *alive, float *total,
@@ -448,9 +494,10 @@ __global__ void get_state_kernel(const __grid_constant__ StepParams P, float *go
     if (env >= P.n) return;
     const int J = P.n_joints;
     if (goals) for (int i = 0; i < J; ++i) goals[env * J + i] = P.goals[env * J + i];
-    if (alive) alive[env] = P.alive[env];
+    const uint32_t w = P.alive[env];
+    if (alive) alive[env] = alive_mask_of(P, w);
     if (total) total[env] = P.total_reward[env];
-    if (eplen) eplen[env] = (int32_t)(P.counters[env] & 0xffffu);
+    if (eplen) eplen[env] = (int32_t)(P.ep_shift ? (w >> P.ep_shift) : P.counters[env]);
 }
 
 __global__ void sample_actions_kernel(const __grid_constant__ StepParams P, float *actions) {
@@ -480,8 +527,15 @@ __global__ void stats_kernel(const __grid_constant__ StepParams P, long long env
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if (lane == 0) atomicAdd((unsigned long long *)(out + 7), (unsigned long long)local);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 7)
+    if (blockIdx.x == 0 && threadIdx.x < 6)
         out[threadIdx.x] = threadIdx.x == 0 ? env_steps : (long long)P.stats[threadIdx.x];
+    if (blockIdx.x == 0 && warp == 1) {          // ground-contact steps: the per-warp slots of the step kernel
+        long long g = 0;
+        for (int i = lane; i < kGroundSlots; i += 32) g += (long long)P.stats[MT_STATS_WORDS + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) out[6] = g + (long long)P.stats[6];
+    }
 }
 
 __global__ void fk_kernel(const __grid_constant__ StepParams P, int mode, const float *goals, long long m, float *out) {
@@ -831,6 +885,7 @@ extern "C" int mt_fetch_env(mt_env *e, int64_t index, float *goals_host, float *
     CU(cudaDeviceSynchronize());
     uint32_t alive = 0;
     CU(cudaMemcpy(&alive, e->alive + index, 4, cudaMemcpyDeviceToHost));
+    alive = alive_mask_of(e->base, alive);
     if (alive_host) *alive_host = alive;
     if (goals_host) CU(cudaMemcpy(goals_host, e->goals + index * J, J * 4, cudaMemcpyDeviceToHost));
     if (total_reward_host) CU(cudaMemcpy(total_reward_host, e->total_reward + index, 4, cudaMemcpyDeviceToHost));
@@ -882,7 +937,7 @@ extern "C" int mt_stats_host(mt_env *e, mt_stats *out) {
 extern "C" int mt_stats_clear(mt_env *e, void *stream) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
     DeviceGuard guard(e->cfg.device);
-    CU(cudaMemsetAsync(e->stats, 0, MT_STATS_WORDS * 8, (cudaStream_t)stream));
+    CU(cudaMemsetAsync(e->stats, 0, (MT_STATS_WORDS + kGroundSlots) * 8, (cudaStream_t)stream));
     e->env_steps = 0;
     return MT_OK;
 }

@@ -56,7 +56,13 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
     return p;
 }
 __device__ __forceinline__ uint64_t policy_evict_first() { return policy_evict_last(); }
+__device__ __forceinline__ uint64_t policy_evict_normal() { return policy_evict_last(); }
 #else
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -72,6 +78,11 @@ __device__ __forceinline__ float4 ld_hint(const float4 *a, uint64_t pol) {
     float4 v;
     asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float2 ld_hint(const float2 *a, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.x), "=f"(v.y) : "l"(a), "l"(pol));
     return v;
 }
 __device__ __forceinline__ float ld_hint(const float *a, uint64_t pol) {

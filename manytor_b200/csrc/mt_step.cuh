@@ -28,6 +28,11 @@ namespace mt {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kTile = 32;
+// Ground-contact steps are counted per warp and added, once per launch, to one of kGroundSlots
+// counters behind the statistics words (slot = global warp index mod kGroundSlots): every warp of
+// a grid finishing with an atomic on ONE address was measured at +3.6 us per launch (4144
+// same-address atomics serialising in the launch's tail); spread over 2048 addresses they are free.
+constexpr int kGroundSlots = 2048;
 
 enum StepFlags : int32_t {
     kTerminateOnGround = 1,
@@ -43,9 +48,9 @@ struct JointConst {
 struct StepParams {
     // state (HBM, padded to a whole number of tiles)
     float *goals;            // [Npad][J]
-    uint32_t *alive;         // [Npad]
+    uint32_t *alive;         // [Npad]  packed layout: alive mask (bits < ep_shift) | ep_len << ep_shift; wide: mask only
     float *total_reward;     // [Npad]
-    uint32_t *counters;      // [Npad]  ep_len (low 16, saturating) | ground steps (high 16, saturating)
+    uint32_t *counters;      // [Npad]  wide layout only: ep_len (saturating at ep_max); nullptr when packed
     uint32_t *episode;       // [Npad]  resets so far (touched only on reset)
     float *points;           // [Npad][X][3]
     // per-step I/O
@@ -70,7 +75,23 @@ struct StepParams {
     JointConst arm[MT_MAX_JOINTS];
     uint32_t tile_bytes;
     int32_t pair_layout;     // objectives stored pair-interleaved (see point_index)
+    // Episode length: packed into the alive word above the mask when it fits (every X <= 16; X < 32 when
+    // the horizon fits in the 32 - X spare bits), which saves one 4-byte state array read and written per
+    // step; otherwise (ep_shift == 0) it lives in `counters`.  Saturates at ep_max either way.
+    int32_t ep_shift;
+    uint32_t ep_max;
+    // Tiles below keep_tiles mark their per-env state evict_last (it stays in the 126 MB L2 from one step
+    // to the next); beyond it the state is cached evict_normal, because protecting more lines than the L2
+    // can hold costs more than no hint at all (tools/microbench/bigstreams.cu, N = 2^22).
+    long long keep_tiles;
+    // createpolicy results (evict_last / evict_normal / evict_first), made once per handle and passed as
+    // constants so that the step kernel does not hold six registers for them across its whole tile loop
+    unsigned long long pol_last, pol_normal, pol_stream;
 };
+
+__host__ __device__ __forceinline__ uint32_t alive_mask_of(const StepParams &P, uint32_t word) {
+    return P.ep_shift ? (word & ((1u << P.ep_shift) - 1u)) : word;
+}
 
 // ---------------------------------------------------------------------------
 // kinematics
@@ -538,20 +559,26 @@ __device__ __forceinline__ void draw_actions(const StepParams &P, long long gid,
 template <int J>
 struct TileScalars {
     float g[J], a[J];
-    uint32_t alive;
+    uint32_t alive;   // the state word: alive mask (| ep_len << ep_shift in the packed layout)
     float total;
-    uint32_t cnt;
+    uint32_t cnt;     // ep_len in the wide layout
 };
 
 template <int J, bool RAND>
 __device__ __forceinline__ void load_scalars(const StepParams &P, long long env, TileScalars<J> &s, uint64_t keep,
                                              uint64_t stream) {
+    // goals[0] is never loaded: no sub-pose z depends on joint 0 (it turns about the world z axis), so
+    // the register of a prefetched goals[0] would be dead on arrival, ptxas would hand it out as scratch
+    // at once, and that write-after-write hazard parks the warp on the prefetch's full memory latency
+    // (it was 21 % of all stall samples in ncu with a 128-bit load of the whole row).
+    s.g[0] = 0.f;
     if (J == 4) {
-        float4 t = ld_hint(reinterpret_cast<const float4 *>(P.goals + env * 4), keep);
-        s.g[0] = t.x; s.g[1] = t.y; s.g[2] = t.z; s.g[3] = t.w;
+        s.g[1] = ld_hint(P.goals + env * 4 + 1, keep);
+        float2 t = ld_hint(reinterpret_cast<const float2 *>(P.goals + env * 4 + 2), keep);
+        s.g[2] = t.x; s.g[3] = t.y;
     } else {
 #pragma unroll
-        for (int i = 0; i < J; ++i) s.g[i] = ld_hint(P.goals + env * J + i, keep);
+        for (int i = 1; i < J; ++i) s.g[i] = ld_hint(P.goals + env * J + i, keep);
     }
     if (!RAND) {
         if (env >= P.n) {
@@ -567,7 +594,7 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, long long env,
     }
     s.alive = ld_hint(P.alive + env, keep);
     s.total = ld_hint(P.total_reward + env, keep);
-    s.cnt = ld_hint(P.counters + env, keep);
+    s.cnt = P.ep_shift ? 0u : ld_hint(P.counters + env, keep);
 }
 
 // ---------------------------------------------------------------------------
@@ -608,7 +635,8 @@ step_kernel(const __grid_constant__ StepParams P) {
     // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
     // tiles (a single ticket counter was measured first: ~37k same-address atomics per launch
     // serialise in L2 and cost more than the imbalance they remove).
-    const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    const uint64_t pol_stream = P.pol_stream;
+    auto state_policy = [&](long long tile) -> uint64_t { return tile < P.keep_tiles ? P.pol_last : P.pol_normal; };
     const long long total_warps = (long long)gridDim.x * kWarpsPerBlock;
     const long long first = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
     auto fetch_points = [&](long long tile, int b) {   // lane 0 only
@@ -628,10 +656,12 @@ step_kernel(const __grid_constant__ StepParams P) {
     if (lane == 0) fetch_points(cur, 0);
     __syncwarp();
     TileScalars<J> sc;
-    load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
+    load_scalars<J, RAND>(P, cur * kTile + lane, sc, state_policy(cur), pol_stream);
     long long nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
     int b = 0;
     uint32_t phase0 = 0, phase1 = 0;
+    const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
+    uint32_t ground_steps = 0;              // warp-uniform: ground-contact env-steps of this warp's tiles
 
     while (true) {
         const long long env0 = cur * kTile, env = env0 + lane;
@@ -640,7 +670,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 
         // 1. next tile's scalars on their way to registers
         TileScalars<J> sn;
-        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
+        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, state_policy(nxt), pol_stream);
 
         // 2. kinematics of the current tile (needs no objectives)
         if (RAND) draw_actions(P, P.env_id_base + env, J, sc.a);
@@ -662,7 +692,7 @@ step_kernel(const __grid_constant__ StepParams P) {
         mbar_wait(bar + b, b ? phase1 : phase0);
         if (b) phase1 ^= 1u; else phase0 ^= 1u;
         float *row = tile_buf(b) + lane * rowlen;
-        const uint32_t alive0 = sc.alive;
+        const uint32_t alive0 = sc.alive & amask;
         const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
         uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
 
@@ -670,8 +700,8 @@ step_kernel(const __grid_constant__ StepParams P) {
         float rew = (alive1 != alive0) ? 1.0f : 0.0f;
         rew = neg ? -1.0f : rew;
         float total = sc.total + rew;
-        uint32_t eplen = min((sc.cnt & 0xffffu) + 1u, 0xffffu);
-        uint32_t gsteps = min((sc.cnt >> 16) + (neg ? 1u : 0u), 0xffffu);
+        uint32_t eplen = min((P.ep_shift ? sc.alive >> P.ep_shift : sc.cnt) + 1u, P.ep_max);
+        ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
         bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
         bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
         const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
@@ -691,13 +721,11 @@ step_kernel(const __grid_constant__ StepParams P) {
             atomicAdd(P.stats + 3, (unsigned long long)(long long)total);
             atomicAdd(P.stats + 4, (unsigned long long)eplen);
             atomicAdd(P.stats + 5, (unsigned long long)(x - __popc(alive1)));
-            atomicAdd(P.stats + 6, (unsigned long long)gsteps);
 #pragma unroll
             for (int i = 0; i < J; ++i) gn[i] = 0.f;
             alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
             total = 0.f;
             eplen = 0u;
-            gsteps = 0u;
         }
         while (pending) {
             const int src = __ffs(pending) - 1;
@@ -731,15 +759,16 @@ step_kernel(const __grid_constant__ StepParams P) {
         __syncwarp();
 
         // 7. write back: state (coalesced), then the observation tile by one bulk store
+        const uint64_t pol_keep = state_policy(cur);
         if (J == 4) {
             st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
         } else {
 #pragma unroll
             for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, gn[i], pol_keep);
         }
-        st_hint(P.alive + env, alive1, pol_keep);
+        st_hint(P.alive + env, P.ep_shift ? (alive1 | (eplen << P.ep_shift)) : alive1, pol_keep);
         st_hint(P.total_reward + env, total, pol_keep);
-        st_hint(P.counters + env, eplen | (gsteps << 16), pol_keep);
+        if (!P.ep_shift) st_hint(P.counters + env, eplen, pol_keep);
         if (valid) {
             st_hint(P.reward + env, rew, pol_stream);
             st_hint(P.done + env, done, pol_stream);
@@ -776,6 +805,9 @@ step_kernel(const __grid_constant__ StepParams P) {
         if (NB == 2) b ^= 1;
         __syncwarp();
     }
+    if (lane == 0 && ground_steps)
+        atomicAdd(P.stats + MT_STATS_WORDS + ((blockIdx.x * kWarpsPerBlock + warp) & (kGroundSlots - 1)),
+                  (unsigned long long)ground_steps);
     if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
 }
 

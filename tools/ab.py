@@ -1,22 +1,39 @@
 #!/usr/bin/env python
-"""A/B timing of two builds of libmanytor_b200.so in ONE process on ONE GPU, interleaved
-round by round so that clocks, temperature and the box are the same for both.
-  python tools/ab.py tools/ab/A.so tools/ab/B.so [rounds]"""
-import os, sys, time
+"""A/B timing of several builds of libmanytor_b200.so in ONE process on ONE GPU, interleaved
+round by round so that clocks, temperature and the box are the same for all of them.
+  python tools/ab.py [--lg 20] [--x 10] [--arm ref|ur5] [--rounds 6] [--steps 400] A.so B.so[@keep_mb] [C.so ...]"""
+import argparse, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from manytor_b200 import BatchedEnvs
+from manytor_b200 import BatchedEnvs, REFERENCE_ARM, UR5_ARM
 
-paths = [os.path.abspath(p) for p in sys.argv[1:3]]
-rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 6
-n, K = 1 << 20, 400
+ap = argparse.ArgumentParser()
+ap.add_argument("libs", nargs="+")
+ap.add_argument("--lg", type=int, default=20)
+ap.add_argument("--x", type=int, default=10)
+ap.add_argument("--arm", default="ref")
+ap.add_argument("--rounds", type=int, default=6)
+ap.add_argument("--steps", type=int, default=400)
+ap.add_argument("--modes", default="step,rand,noobs")
+args = ap.parse_args()
+
+# "lib.so@48" = create that handle with MT_L2_KEEP_MB=48 (evict_last budget for the per-env state)
+specs = [(p.split("@") + [None])[:2] for p in args.libs]
+paths = [os.path.abspath(p) for p, _ in specs]
+names = [os.path.basename(p) + (("@" + k) if k else "") for p, k in specs]
+n, K = 1 << args.lg, args.steps
+arm = UR5_ARM if args.arm == "ur5" else REFERENCE_ARM
+J = arm.n_joints
 envs = []
-for p in paths:
-    e = BatchedEnvs(n, 10, device=0, auto_reset=True, horizon=1000, seed=1, lib_path=p)
+for p, (_, keep) in zip(paths, specs):
+    os.environ.pop("MT_L2_KEEP_MB", None)
+    if keep:
+        os.environ["MT_L2_KEEP_MB"] = keep
+    e = BatchedEnvs(n, args.x, arm=arm, device=0, auto_reset=True, horizon=1000, seed=1, lib_path=p)
     e.reset()
     e.rollout_random(1000, write_obs=False)
     envs.append(e)
-acts = [torch.randint(-180, 180, (n, 4), device="cuda").float() for _ in range(16)]
+acts = [torch.randint(-180, 180, (n, J), device="cuda").float() for _ in range(8)]
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 while time.perf_counter() - t0 < 1.5:
@@ -30,17 +47,19 @@ def run(fn):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) * 1e3 / K
 
-modes = {
-    "step(actions from HBM), obs": lambda e: [e.step(acts[i & 15]) for i in range(K)],
-    "rollout_random, obs": lambda e: e.rollout_random(K),
-    "rollout_random, no obs": lambda e: e.rollout_random(K, write_obs=False),
+all_modes = {
+    "step": ("step(actions from HBM), obs", lambda e: [e.step(acts[i & 7]) for i in range(K)]),
+    "rand": ("rollout_random, obs", lambda e: e.rollout_random(K)),
+    "noobs": ("rollout_random, no obs", lambda e: e.rollout_random(K, write_obs=False)),
 }
+modes = {all_modes[m][0]: all_modes[m][1] for m in args.modes.split(",")}
 res = {m: [[] for _ in envs] for m in modes}
-for r in range(rounds):
+for r in range(args.rounds):
     for m, fn in modes.items():
         for i, e in enumerate(envs):
             res[m][i].append(run(lambda: fn(e)))
+print(f"N = 2^{args.lg} envs, x = {args.x}, arm = {args.arm}, {K} steps x {args.rounds} rounds")
 for m in modes:
     for i, p in enumerate(paths):
         v = sorted(res[m][i])
-        print(f"{m:32s} {os.path.basename(p):12s} median {v[len(v)//2]:.2f} us/step  min {v[0]:.2f}  max {v[-1]:.2f}")
+        print(f"{m:32s} {names[i]:20s} median {v[len(v)//2]:8.2f} us/step  min {v[0]:8.2f}  max {v[-1]:8.2f}")
