@@ -65,6 +65,7 @@ struct mt_env {
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;
+    float keep_fraction = 1.f; // share of the state lines marked evict_last (StepParams::pol_state)
     int32_t ep_shift = 0;      // > 0: ep_len packed into the alive word above bit ep_shift
     uint32_t ep_max = 65535u;
     int num_sms = 0;
@@ -150,10 +151,14 @@ extern "C" int mt_config_init(mt_config *cfg) {
     return MT_OK;
 }
 
-__global__ void policy_kernel(unsigned long long *out) {
-    out[0] = policy_evict_last();
-    out[1] = policy_evict_normal();
-    out[2] = policy_evict_first();
+// the two L2 eviction policies of a handle (StepParams::pol_state / pol_stream)
+__global__ void policy_kernel(unsigned long long *out, float keep_fraction) {
+#ifdef MT_NO_L2_HINTS
+    out[0] = out[1] = policy_evict_last();      // A/B builds: evict_normal everywhere
+#else
+    out[0] = keep_fraction > 0.f ? policy_evict_last_fraction(fminf(keep_fraction, 1.0f)) : policy_evict_normal();
+    out[1] = policy_evict_first();
+#endif
 }
 
 static int validate(const mt_config &c) {
@@ -298,8 +303,13 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.ep_shift = e->ep_shift;
     e->base.ep_max = e->ep_max;
     {
-        policy_kernel<<<1, 1>>>(e->stats);                       // stats words are zeroed again right below
-        unsigned long long pol[3] = {0, 0, 0};
+        // evict_last budget for the per-env state: 36 MB of the 126 MB L2 (MT_L2_KEEP_MB overrides, 0 = none)
+        double keep_mb = 36.0;
+        if (const char *kb = std::getenv("MT_L2_KEEP_MB")) keep_mb = std::atof(kb);
+        const double state_bytes = (4.0 * J + 8.0 + (e->ep_shift ? 0.0 : 4.0)) * (double)np;
+        e->keep_fraction = (float)(keep_mb * 1048576.0 >= state_bytes ? 1.0 : keep_mb * 1048576.0 / state_bytes);
+        policy_kernel<<<1, 1>>>(e->stats, e->keep_fraction);    // the stats words are zeroed again right below
+        unsigned long long pol[2] = {0, 0};
         cudaError_t pe = cudaMemcpy(pol, e->stats, sizeof(pol), cudaMemcpyDeviceToHost);
         if (pe == cudaSuccess) pe = cudaMemset(e->stats, 0, sizeof(pol));
         if (pe != cudaSuccess) {
@@ -307,14 +317,8 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
             mt_destroy(e);
             return rc;
         }
-        e->base.pol_last = pol[0]; e->base.pol_normal = pol[1]; e->base.pol_stream = pol[2];
-    }
-    {
-        // evict_last budget for the per-env state: 36 MB of the 126 MB L2 (MT_L2_KEEP_MB overrides, 0 = none)
-        double keep_mb = 36.0;
-        if (const char *kb = std::getenv("MT_L2_KEEP_MB")) keep_mb = std::atof(kb);
-        const double state_bytes = 4.0 * J + 8.0 + (e->ep_shift ? 0.0 : 4.0);
-        e->base.keep_tiles = (long long)(keep_mb * 1048576.0 / state_bytes) / kTile;
+        e->base.pol_state = pol[0];
+        e->base.pol_stream = pol[1];
     }
     // Run-time specialisation (mt_jit.cuh): a run-time table with the usual frame selectors gets its own
     // Preset<>; a built-in arm with an objective count other than the pre-compiled 10 / 20 gets the same arm

@@ -56,13 +56,7 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
     return p;
 }
 __device__ __forceinline__ uint64_t policy_evict_first() { return policy_evict_last(); }
-__device__ __forceinline__ uint64_t policy_evict_normal() { return policy_evict_last(); }
 #else
-__device__ __forceinline__ uint64_t policy_evict_normal() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -74,6 +68,18 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     return p;
 }
 #endif
+// evict_last for `fraction` of the lines it is applied to (picked by address hash, so always the same
+// lines), the default evict_normal for the rest; fraction in (0, 1]
+__device__ __forceinline__ uint64_t policy_evict_last_fraction(float fraction) {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ float4 ld_hint(const float4 *a, uint64_t pol) {
     float4 v;
     asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"

@@ -80,13 +80,14 @@ struct StepParams {
     // step; otherwise (ep_shift == 0) it lives in `counters`.  Saturates at ep_max either way.
     int32_t ep_shift;
     uint32_t ep_max;
-    // Tiles below keep_tiles mark their per-env state evict_last (it stays in the 126 MB L2 from one step
-    // to the next); beyond it the state is cached evict_normal, because protecting more lines than the L2
-    // can hold costs more than no hint at all (tools/microbench/bigstreams.cu, N = 2^22).
-    long long keep_tiles;
-    // createpolicy results (evict_last / evict_normal / evict_first), made once per handle and passed as
-    // constants so that the step kernel does not hold six registers for them across its whole tile loop
-    unsigned long long pol_last, pol_normal, pol_stream;
+    // L2 eviction policies (createpolicy results), made once per handle and passed as constants, so the
+    // step kernel holds no registers for them across its tile loop.  pol_state marks the per-env state
+    // evict_last so that it stays in the 126 MB L2 from one step to the next -- for the FRACTION of its
+    // lines (chosen by the hardware's address hash, hence the same lines every step) that fits the
+    // handle's L2 budget: protecting more lines than the L2 can hold costs more than no hint at all
+    // (tools/microbench/bigstreams.cu, N = 2^22).  pol_stream (evict_first) is for everything that
+    // passes through once per step: actions, objectives, observations, reward, done.
+    unsigned long long pol_state, pol_stream;
 };
 
 __host__ __device__ __forceinline__ uint32_t alive_mask_of(const StepParams &P, uint32_t word) {
@@ -635,8 +636,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
     // tiles (a single ticket counter was measured first: ~37k same-address atomics per launch
     // serialise in L2 and cost more than the imbalance they remove).
-    const uint64_t pol_stream = P.pol_stream;
-    auto state_policy = [&](long long tile) -> uint64_t { return tile < P.keep_tiles ? P.pol_last : P.pol_normal; };
+    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
     const long long total_warps = (long long)gridDim.x * kWarpsPerBlock;
     const long long first = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
     auto fetch_points = [&](long long tile, int b) {   // lane 0 only
@@ -656,7 +656,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     if (lane == 0) fetch_points(cur, 0);
     __syncwarp();
     TileScalars<J> sc;
-    load_scalars<J, RAND>(P, cur * kTile + lane, sc, state_policy(cur), pol_stream);
+    load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
     long long nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
     int b = 0;
     uint32_t phase0 = 0, phase1 = 0;
@@ -670,7 +670,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 
         // 1. next tile's scalars on their way to registers
         TileScalars<J> sn;
-        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, state_policy(nxt), pol_stream);
+        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
         // 2. kinematics of the current tile (needs no objectives)
         if (RAND) draw_actions(P, P.env_id_base + env, J, sc.a);
@@ -759,7 +759,6 @@ step_kernel(const __grid_constant__ StepParams P) {
         __syncwarp();
 
         // 7. write back: state (coalesced), then the observation tile by one bulk store
-        const uint64_t pol_keep = state_policy(cur);
         if (J == 4) {
             st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
         } else {

@@ -372,15 +372,19 @@ def test_step_host_equals_device_step(mt):
         np.testing.assert_array_equal(da.cpu().numpy(), db)
 
 
-def test_state_roundtrip_and_dead_points(mt):
-    n, x = 77, 10
-    env = mt.BatchedEnvs(n, x, device=0, seed=3)
+@pytest.mark.parametrize("x,horizon,ep_hi", [(10, 0, 65536), (16, 0, 65536), (20, 0, 65536), (20, 1000, 4096), (29, 5, 8),
+                                             (32, 1000, 65536)])
+def test_state_roundtrip_and_dead_points(mt, x, horizon, ep_hi):
+    """set_state / get_state / get_points / observe / fetch_env, for every layout of the state word
+    (ep_len above the alive mask at bit 16, bit 20, bit 29; or in its own array)."""
+    n = 77
+    env = mt.BatchedEnvs(n, x, device=0, seed=3, horizon=horizon)
     env.reset()
     rng = np.random.RandomState(2)
     goals = rng.uniform(-180, 180, size=(n, 4)).astype(np.float32)
     alive = rng.rand(n, x) > 0.4
     tot = rng.randint(-50, 5, size=n).astype(np.float32)
-    ep = rng.randint(0, 1000, size=n).astype(np.int32)
+    ep = rng.randint(0, ep_hi, size=n).astype(np.int32)
     env.set_state(goals=goals, alive=alive, total_reward=tot, ep_len=ep)
     st = env.get_state()
     np.testing.assert_array_equal(st["goals"].cpu().numpy(), goals)
@@ -397,6 +401,41 @@ def test_state_roundtrip_and_dead_points(mt):
     np.testing.assert_array_equal(f["goals"], goals[5])
     from oracle.manytor_oracle import joints_coordinates
     np.testing.assert_allclose(f["joints_coordinates"], joints_coordinates(goals[5].astype(np.float64)), atol=5.6e-4)
+    # partial updates leave the other half of the state word alone; ep_len saturates, never wraps into the mask
+    env.set_state(ep_len=np.full(n, 10 ** 6, np.int32))
+    st = env.get_state()
+    np.testing.assert_array_equal(alive_bits_to_matrix(st["alive"].cpu().numpy(), x), alive)
+    assert np.all(st["ep_len"].cpu().numpy() == ep_hi - 1)
+    env.set_state(alive=~alive)
+    st = env.get_state()
+    np.testing.assert_array_equal(alive_bits_to_matrix(st["alive"].cpu().numpy(), x), ~alive)
+    assert np.all(st["ep_len"].cpu().numpy() == ep_hi - 1)
+    act = rng.randint(-180, 180, size=(n, 4)).astype(np.float32)
+    env.step(act)                                                   # one step at the saturated counter
+    st = env.get_state()
+    assert np.all(st["ep_len"].cpu().numpy() == ep_hi - 1)
+    assert np.all(alive_bits_to_matrix(st["alive"].cpu().numpy(), x) <= ~alive)
+
+
+def test_state_layouts_agree(mt):
+    """x = 20 with a horizon that fits the 12 spare bits of the alive word (packed layout) and with
+    no horizon (episode length in its own array) must produce bit-identical steps."""
+    n, x = 1000, 20
+    outs = []
+    for horizon in (4000, 0):
+        env = mt.BatchedEnvs(n, x, device=0, seed=11, horizon=horizon, auto_reset=True)
+        env.reset()
+        acc = []
+        for t in range(120):
+            obs, rew, done = env.rollout_random(1)
+            acc.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), done.cpu().numpy().copy()))
+        st = env.get_state()
+        outs.append((acc, {k: v.cpu().numpy() for k, v in st.items()}, env.stats()))
+    for (o1, r1, d1), (o2, r2, d2) in zip(outs[0][0], outs[1][0]):
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(d1, d2)
+    for k in outs[0][1]:
+        np.testing.assert_array_equal(outs[0][1][k], outs[1][1][k])
+    assert outs[0][2] == outs[1][2]
 
 
 # --------------------------------------------------------------------------
@@ -438,10 +477,13 @@ def test_non_standard_frame_selectors(mt):
     assert rep.ok(), rep.notes[:5]
 
 
-@pytest.mark.parametrize("n,x,tog", [(77, 32, False), (45, 10, True), (130, 3, False)])
+@pytest.mark.parametrize("n,x,tog", [(77, 32, False), (45, 10, True), (130, 3, False), (70, 20, False), (33, 29, False),
+                                     (50, 31, False)])
 def test_auto_reset_tail_tiles_and_ground_termination(mt, n, x, tog):
     """In-kernel reset on ragged shards, the maximum objective count, and README-style termination
-    on ground contact: every reset must restore the reference's reset() state (manytor.py:219-241)."""
+    on ground contact: every reset must restore the reference's reset() state (manytor.py:219-241).
+    The cases cover both state layouts: episode length inside the alive word (x <= 16; x = 20 and
+    x = 29, whose spare bits hold the horizon) and in its own array (x = 31, 32)."""
     horizon = 6
     env = mt.BatchedEnvs(n, x, device=0, auto_reset=True, horizon=horizon, terminate_on_ground=tog, seed=n)
     env.reset()

@@ -15,7 +15,28 @@ ap.add_argument("--arm", default="ref")
 ap.add_argument("--rounds", type=int, default=6)
 ap.add_argument("--steps", type=int, default=400)
 ap.add_argument("--modes", default="step,rand,noobs")
+ap.add_argument("--isolate", type=int, default=0, metavar="REPS",
+                help="one PROCESS per library, REPS passes over the list (A B C A B C ...): handles that share a "
+                     "process also share the L2, and the evict_last state lines of the idle ones stay resident")
 args = ap.parse_args()
+
+if args.isolate:
+    import re, subprocess
+    base = [sys.executable, os.path.abspath(__file__), "--lg", str(args.lg), "--x", str(args.x), "--arm", args.arm,
+            "--rounds", str(args.rounds), "--steps", str(args.steps), "--modes", args.modes]
+    acc = {}
+    for rep in range(args.isolate):
+        for lib in args.libs:
+            out = subprocess.run(base + [lib], capture_output=True, text=True).stdout
+            for line in out.splitlines():
+                m = re.match(r"(.{32}) (\S+)\s+median\s+([0-9.]+)", line)
+                if m:
+                    acc.setdefault((m.group(1), lib), []).append(float(m.group(3)))
+    print(f"N = 2^{args.lg} envs, x = {args.x}, arm = {args.arm}, {args.steps} steps x {args.rounds} rounds, "
+          f"{args.isolate} isolated processes per library (medians of each)")
+    for (mode, lib), v in acc.items():
+        print(f"{mode} {os.path.basename(lib):20s} " + "  ".join(f"{t:7.2f}" for t in v) + f"   best {min(v):7.2f} us/step")
+    sys.exit(0)
 
 # "lib.so@48" = create that handle with MT_L2_KEEP_MB=48 (evict_last budget for the per-env state)
 specs = [(p.split("@") + [None])[:2] for p in args.libs]
