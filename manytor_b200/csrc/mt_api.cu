@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <unordered_map>
+#include <utility>
 
 #include "mt_jit.cuh"
 #include "mt_step.cuh"
@@ -69,7 +70,7 @@ struct mt_env {
     int32_t ep_shift = 0;      // > 0: ep_len packed into the alive word above bit ep_shift
     uint32_t ep_max = 65535u;
     int num_sms = 0;
-    std::unordered_map<const void *, int> blocks_per_sm;   // occupancy of each step-kernel variant, queried once
+    std::unordered_map<const void *, int> block_shape;   // per step-kernel variant: most warps one block can have on an SM
     const float *obj_stream = nullptr;
     int32_t obj_sets = 0;
     unsigned long long step_index = 0;
@@ -663,26 +664,45 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
         fn = (const void *)pick_kernel(e->arm, e->cfg.n_obj, rnd, wobs);
     }
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
+    // Block shape: as many warps as ONE block can have on an SM (they share the block's tile queue), bounded
+    // by the kernel's __launch_bounds__ and by shared memory (nb tile buffers + nb mbarriers per warp);
+    // MT_WARPS_PER_BLOCK overrides the target (tuning / A-B runs).
     const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
-    const size_t smem = nb * kWarpsPerBlock * P.tile_bytes + nb * kWarpsPerBlock * sizeof(uint64_t);
-    int per_sm = 0;
-    auto hit = e->blocks_per_sm.find(fn);
-    if (hit != e->blocks_per_sm.end()) {
-        per_sm = hit->second;
+    const size_t per_warp = nb * P.tile_bytes + nb * sizeof(uint64_t);
+    int max_wpb = 0;
+    auto hit = e->block_shape.find(fn);
+    if (hit != e->block_shape.end()) {
+        max_wpb = hit->second;
     } else {
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * kTile, smem));
-        if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (smem %zu B)", smem);
-        e->blocks_per_sm[fn] = per_sm;
+        max_wpb = e->arm == 0 ? kMaxWarpsRefArm : kMaxWarpsGeneric;
+        if (const char *w = std::getenv("MT_WARPS_PER_BLOCK")) {
+            const int v = std::atoi(w);
+            if (v >= 1 && v <= max_wpb) max_wpb = v;
+        }
+        const size_t smem_cap = 227 * 1024 - 2048;                // per-SM limit minus the per-block reserve
+        if ((size_t)max_wpb * per_warp > smem_cap) max_wpb = (int)(smem_cap / per_warp);
+        if (max_wpb < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (%zu B of shared memory per warp)", per_warp);
+        const size_t smem_max = (size_t)max_wpb * per_warp;
+        if (smem_max > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, max_wpb * kTile, smem_max));
+        if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (%d warps, %zu B of shared memory)", max_wpb, smem_max);
+        e->block_shape[fn] = max_wpb;
     }
+    // A launch with fewer tiles than max_wpb x SMs (small shards, the chunks of mt_step_host) uses smaller
+    // blocks, several per SM, so that it still spreads over every SM.
     const long long tiles = t1 - t0;
-    const long long want = (tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    long long fair = (tiles + e->num_sms - 1) / e->num_sms;
+    const int wpb = (int)(fair < 1 ? 1 : (fair > max_wpb ? max_wpb : fair));
+    const int per_sm = max_wpb / wpb;                             // registers and shared memory scale with the warps
+    const size_t smem = (size_t)wpb * per_warp;
+    const long long want = (tiles + wpb - 1) / wpb;
     const long long cap = (long long)per_sm * e->num_sms;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     // programmatic dependent launch: see griddep_wait() in mt_ptx.cuh
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kWarpsPerBlock * kTile);
+    lc.blockDim = dim3(wpb * kTile);
     lc.dynamicSmemBytes = smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1021,3 +1041,12 @@ extern "C" int mt_last_kernel_ms(mt_env *e, float *ms_out) {
     CU(cudaEventElapsedTime(ms_out, e->ev0, e->ev1));
     return MT_OK;
 }
+
+#ifdef MT_TRACE
+// debug builds only (nvcc -DMT_TRACE): per-warp trace of the most recent step launches, [kTraceWarps][4] u64
+extern "C" int mt_debug_trace(unsigned long long *out_host) {
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * kTraceWarps * 4));
+    return MT_OK;
+}
+#endif

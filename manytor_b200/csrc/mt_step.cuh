@@ -26,8 +26,11 @@
 
 namespace mt {
 
-constexpr int kWarpsPerBlock = 4;
 constexpr int kTile = 32;
+// Warps per block is a launch-time choice (blockDim.x / 32): as many as one SM can hold in ONE block (28
+// for the reference arm at x = 10: 72 registers, 7.7 KB of tile buffers per warp), because the warps of a
+// block share the block's tile queue (see step_kernel).  Upper bounds for __launch_bounds__:
+constexpr int kMaxWarpsRefArm = 28, kMaxWarpsGeneric = 16;
 // Ground-contact steps are counted per warp and added, once per launch, to one of kGroundSlots
 // counters behind the statistics words (slot = global warp index mod kGroundSlots): every warp of
 // a grid finishing with an atomic on ONE address was measured at +3.6 us per launch (4144
@@ -614,12 +617,23 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, long long env,
 // ---------------------------------------------------------------------------
 template <int ARM> struct StepBuffers { static constexpr int value = (ARM == 0) ? 2 : 1; };
 
+#ifdef MT_TRACE   // tools/trace_warps.py: per-warp (start ns, end ns, SM id, tiles done) of the last launch
+constexpr int kTraceWarps = 8192;
+__device__ unsigned long long g_trace[kTraceWarps * 4];
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 template <int ARM, int X, bool RAND, bool WOBS>
-__global__ void __launch_bounds__(kWarpsPerBlock *kTile, (ARM == 0) ? 7 : 4)
+__global__ void __launch_bounds__(((ARM == 0) ? kMaxWarpsRefArm : kMaxWarpsGeneric) * kTile, 1)
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int queue_next;
     constexpr int J = ArmJoints<ARM>::value;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int x = X ? X : P.n_obj;
     const int rowlen = 3 * x;
     const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
@@ -630,23 +644,40 @@ step_kernel(const __grid_constant__ StepParams P) {
     constexpr int NB = StepBuffers<ARM>::value;
     unsigned char *tile_base = smem + (size_t)(NB * warp) * P.tile_bytes;
     auto tile_buf = [&](int bb) { return reinterpret_cast<float *>(tile_base + (size_t)bb * P.tile_bytes); };
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(NB * kWarpsPerBlock) * P.tile_bytes) + NB * warp;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(NB * wpb) * P.tile_bytes) + NB * warp;
 
-    // static round-robin tile schedule: warp w of the grid takes tiles w, w + W, w + 2W, ...  Blocks
-    // are placed round-robin over the SMs, so every SM gets the same tile count to within a few
-    // tiles (a single ticket counter was measured first: ~37k same-address atomics per launch
-    // serialise in L2 and cost more than the imbalance they remove).
+    // Tile schedule.  Block b owns the tiles b, b + G, b + 2G, ... (G blocks in the grid, one or two per SM),
+    // and its warps take them from a queue in shared memory as they become free.  A static share per WARP
+    // (the first design) looked balanced -- 7 or 8 tiles each -- but the warp schedulers are not fair: traced
+    // per warp (tools/trace_warps.py), the first warp of an SM finished its 8 tiles in 25 us and the last in
+    // 50 us, so for the second half of every launch the SM ran with ever fewer warps and ever less latency
+    // hiding.  With the queue every warp stays busy until the block's tiles run out.  (One ticket counter
+    // for the whole grid was measured earlier: ~37k same-address global atomics per launch serialise in L2;
+    // a shared-memory atomic per tile costs nothing.)
     const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
-    const long long total_warps = (long long)gridDim.x * kWarpsPerBlock;
-    const long long first = P.tile_begin + (long long)blockIdx.x * kWarpsPerBlock + warp;
+    auto tile_of = [&](int li) -> long long {
+        const long long t = P.tile_begin + (long long)li * gridDim.x + blockIdx.x;
+        return t < P.tile_end ? t : -1;
+    };
+    auto grab_tile = [&]() -> long long {
+        int li = 0;
+        if (lane == 0) li = atomicAdd(&queue_next, 1);
+        return tile_of(__shfl_sync(0xffffffffu, li, 0));
+    };
     auto fetch_points = [&](long long tile, int b) {   // lane 0 only
         mbar_expect_tx(bar + b, tile_bytes);
         bulk_load_hint(tile_buf(b), P.points + tile * kTile * rowlen, tile_bytes, bar + b, pol_stream);
     };
 
-    long long cur = first;
+    if (threadIdx.x == 0) queue_next = wpb;     // the first wpb tiles of the block go to its warps directly
+    __syncthreads();
+    long long cur = tile_of(warp);
+#ifdef MT_TRACE
+    const unsigned long long trace_t0 = trace_now();
+    unsigned trace_tiles = 0;
+#endif
     griddep_launch_dependents();            // the next step's grid may start taking free SM slots
-    if (cur >= P.tile_end) return;
+    if (cur < 0) return;
     if (lane == 0) {
         mbar_init(bar, 1);
         if (NB == 2) mbar_init(bar + 1, 1);
@@ -657,7 +688,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     __syncwarp();
     TileScalars<J> sc;
     load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
-    long long nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
+    long long nxt = grab_tile();
     int b = 0;
     uint32_t phase0 = 0, phase1 = 0;
     const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
@@ -790,6 +821,9 @@ step_kernel(const __grid_constant__ StepParams P) {
             }
         }
 
+#ifdef MT_TRACE
+        ++trace_tiles;
+#endif
         if (nxt < 0) break;
         if (NB == 1) {   // single buffer: refill it as soon as the observations have been read out
             __syncwarp();
@@ -799,13 +833,23 @@ step_kernel(const __grid_constant__ StepParams P) {
             }
         }
         cur = nxt;
-        nxt = cur + total_warps < P.tile_end ? cur + total_warps : -1;
+        nxt = grab_tile();
         sc = sn;
         if (NB == 2) b ^= 1;
         __syncwarp();
     }
+#ifdef MT_TRACE
+    if (lane == 0) {
+        const unsigned w = blockIdx.x * wpb + warp;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (w < kTraceWarps) {
+            g_trace[w * 4] = trace_t0; g_trace[w * 4 + 1] = trace_now(); g_trace[w * 4 + 2] = smid; g_trace[w * 4 + 3] = trace_tiles;
+        }
+    }
+#endif
     if (lane == 0 && ground_steps)
-        atomicAdd(P.stats + MT_STATS_WORDS + ((blockIdx.x * kWarpsPerBlock + warp) & (kGroundSlots - 1)),
+        atomicAdd(P.stats + MT_STATS_WORDS + ((blockIdx.x * wpb + warp) & (kGroundSlots - 1)),
                   (unsigned long long)ground_steps);
     if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
 }

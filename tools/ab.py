@@ -38,7 +38,7 @@ if args.isolate:
         print(f"{mode} {os.path.basename(lib):20s} " + "  ".join(f"{t:7.2f}" for t in v) + f"   best {min(v):7.2f} us/step")
     sys.exit(0)
 
-# "lib.so@48" = create that handle with MT_L2_KEEP_MB=48 (evict_last budget for the per-env state)
+# "lib.so@48" = create that handle with MT_L2_KEEP_MB=48; "lib.so@MT_WARPS_PER_BLOCK=14" sets any variable
 specs = [(p.split("@") + [None])[:2] for p in args.libs]
 paths = [os.path.abspath(p) for p, _ in specs]
 names = [os.path.basename(p) + (("@" + k) if k else "") for p, k in specs]
@@ -47,9 +47,11 @@ arm = UR5_ARM if args.arm == "ur5" else REFERENCE_ARM
 J = arm.n_joints
 envs = []
 for p, (_, keep) in zip(paths, specs):
-    os.environ.pop("MT_L2_KEEP_MB", None)
-    if keep:
-        os.environ["MT_L2_KEEP_MB"] = keep
+    for k in ("MT_L2_KEEP_MB", "MT_WARPS_PER_BLOCK"):
+        os.environ.pop(k, None)
+    for kv in (keep.split(",") if keep else []):     # "48" = MT_L2_KEEP_MB=48; "K=V" sets any variable
+        k, _, v = kv.rpartition("=")
+        os.environ[k or "MT_L2_KEEP_MB"] = v
     e = BatchedEnvs(n, args.x, arm=arm, device=0, auto_reset=True, horizon=1000, seed=1, lib_path=p)
     e.reset()
     e.rollout_random(1000, write_obs=False)
