@@ -71,6 +71,7 @@ struct mt_env {
     uint32_t ep_max = 65535u;
     int num_sms = 0;
     std::unordered_map<const void *, int> block_shape;   // per step-kernel variant: most warps one block can have on an SM
+    std::unordered_map<unsigned long long, int> occupancy;   // (variant, warps per block) -> blocks per SM
     const float *obj_stream = nullptr;
     int32_t obj_sets = 0;
     unsigned long long step_index = 0;
@@ -694,7 +695,18 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     const long long tiles = t1 - t0;
     long long fair = (tiles + e->num_sms - 1) / e->num_sms;
     const int wpb = (int)(fair < 1 ? 1 : (fair > max_wpb ? max_wpb : fair));
-    const int per_sm = max_wpb / wpb;                             // registers and shared memory scale with the warps
+    int per_sm = 1;                                               // blocks of this shape one SM can hold
+    if (wpb < max_wpb || wpb < (e->arm == 0 ? kMaxWarpsRefArm : kMaxWarpsGeneric)) {
+        const unsigned long long key = (unsigned long long)(uintptr_t)fn ^ ((unsigned long long)wpb << 52);
+        auto occ = e->occupancy.find(key);
+        if (occ != e->occupancy.end()) {
+            per_sm = occ->second;
+        } else {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * kTile, (size_t)wpb * per_warp));
+            if (per_sm < 1) per_sm = 1;
+            e->occupancy[key] = per_sm;
+        }
+    }
     const size_t smem = (size_t)wpb * per_warp;
     const long long want = (tiles + wpb - 1) / wpb;
     const long long cap = (long long)per_sm * e->num_sms;

@@ -290,6 +290,62 @@ def test_rollout_random_equals_step_of_sampled_actions(mt):
         assert torch.equal(sa[key], sc[key]), key
 
 
+@pytest.mark.parametrize("n", [150_001, 40_000])
+def test_back_to_back_launches_equal_synchronised_steps(mt, n):
+    """Consecutive step launches hand their work items over block by block (no grid-wide wait between
+    steps, mt_step.cuh): a burst of launches with nothing between them must leave exactly the state,
+    outputs and statistics of the same steps run one at a time -- eagerly, as a replayed CUDA graph, and
+    with the hand-over replaced by stream order.  150 001 envs = full 28-warp blocks on every SM; 40 000 =
+    several smaller blocks per SM."""
+    import torch
+    x, k = 10, 24
+    g = torch.Generator(device="cuda").manual_seed(n)
+    acts = [torch.randint(-180, 180, (n, 4), device="cuda", generator=g).float() for _ in range(k)]
+
+    def fresh():
+        env = mt.BatchedEnvs(n, x, device=0, seed=21, auto_reset=True, horizon=7)
+        env.reset()
+        return env
+
+    def snapshot(env, out):
+        st = env.get_state()
+        return ([v.clone() for v in st.values()], env.get_points(False).clone(), [o.clone() for o in out], env.stats())
+
+    def same(p, q, host_counter=True):
+        sp, sq = dict(p[3]), dict(q[3])
+        if not host_counter:          # env_steps is counted by the host per call, a graph replay does not pass there
+            sp.pop("env_steps"); sq.pop("env_steps")
+        return (all(torch.equal(u, v) for u, v in zip(p[0], q[0])) and torch.equal(p[1], q[1]) and
+                all(torch.equal(u, v) for u, v in zip(p[2], q[2])) and sp == sq)
+
+    ref = fresh()
+    for t in range(2 * k):
+        out = ref.step(acts[t % k])
+        torch.cuda.synchronize()
+    want = snapshot(ref, out)
+
+    burst = fresh()
+    for t in range(2 * k):
+        out = burst.step(acts[t % k])
+    assert same(snapshot(burst, out), want)
+
+    env2 = fresh()
+    env2._out_buffers(True, False)                                           # output buffers exist before capture
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        for t in range(k):
+            out = env2.step(acts[t])
+    cg.replay(); cg.replay()
+    torch.cuda.synchronize()
+    assert same(snapshot(env2, out), want, host_counter=False)
+    out = env2.step(acts[0])                                                 # eager launches after a captured graph
+    out = env2.step(acts[1])
+    out_ref = ref.step(acts[0]); torch.cuda.synchronize()
+    out_ref = ref.step(acts[1]); torch.cuda.synchronize()
+    assert same(snapshot(env2, out), snapshot(ref, out_ref), host_counter=False)
+
+
 def test_shard_invariance(mt):
     """N envs on one handle == the same envs split over two handles (global env ids key the RNG)."""
     import torch

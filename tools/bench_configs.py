@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of every BASELINE.json config that runs on one GPU (configs 2, 3, 5), all modes.
-Device time with CUDA events, 1 s clock warm-up, median of 5 rounds of 300 steps."""
+Device time with CUDA events, 1 s clock warm-up, median of 5 rounds of 300 steps (mt_step: a 300-node CUDA graph)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -26,8 +26,18 @@ def bench(name, n, x, arm, K=300, rounds=5, **kw):
     while time.perf_counter() - t0 < 1.0:
         env.rollout_random(100)
         torch.cuda.synchronize()
+    # K steps with their own action buffers as ONE CUDA graph, like bench.py: Python cannot issue a launch
+    # every ~45 us, and a per-call timing would measure the interpreter
+    env.step(acts[0])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for i in range(K):
+            env.step(acts[i & 7])
+    graph.replay()
+    torch.cuda.synchronize()
     out = {}
-    for mode, fn, hbm_act, wobs in (("step(actions in HBM)", lambda: [env.step(acts[i & 7]) for i in range(K)], True, True),
+    for mode, fn, hbm_act, wobs in (("step(actions in HBM)", graph.replay, True, True),
                                     ("rollout_random", lambda: env.rollout_random(K), False, True),
                                     ("rollout_random, no obs", lambda: env.rollout_random(K, write_obs=False), False, False)):
         ts = []
