@@ -165,7 +165,7 @@ __global__ void policy_kernel(unsigned long long *out, float keep_fraction) {
 
 static int validate(const mt_config &c) {
     if (c.struct_size != sizeof(mt_config)) return fail(MT_ERR_INVALID, "mt_config.struct_size %u != %zu (ABI mismatch)", c.struct_size, sizeof(mt_config));
-    if (c.n_envs < 1) return fail(MT_ERR_INVALID, "n_envs must be >= 1");
+    if (c.n_envs < 1 || c.n_envs > 2000000000LL) return fail(MT_ERR_INVALID, "n_envs must be in [1, 2e9] (32-bit env index per shard)");
     if (c.n_joints < 2 || c.n_joints > MT_MAX_JOINTS) return fail(MT_ERR_INVALID, "n_joints must be in [2, %d]", MT_MAX_JOINTS);
     if (c.n_obj < 1 || c.n_obj > MT_MAX_OBJ) return fail(MT_ERR_INVALID, "n_obj must be in [1, %d]", MT_MAX_OBJ);
     const int J = c.n_joints;

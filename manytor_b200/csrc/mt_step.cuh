@@ -419,8 +419,7 @@ template <bool WOBS>
 __device__ __forceinline__ bool one_objective(float &px, float &py, float &pz, const Frames &f, float tol,
                                               bool alive) {
     // catch: inclusive axis-aligned cube around the catch frame (math.isclose abs_tol)
-    bool caught = (fabsf(f.catcher[0] - px) <= tol) & (fabsf(f.catcher[1] - py) <= tol) &
-                  (fabsf(f.catcher[2] - pz) <= tol);
+    bool caught = fmaxf(fmaxf(fabsf(f.catcher[0] - px), fabsf(f.catcher[1] - py)), fabsf(f.catcher[2] - pz)) <= tol;
     if (WOBS) {
         float dx = fabsf(f.anchor[0] - px), dy = fabsf(f.anchor[1] - py), dz = fabsf(f.anchor[2] - pz);
         float h2 = fmaf(dx, dx, dy * dy);
@@ -454,8 +453,10 @@ template <bool WOBS>
 __device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 PZ, const Frames &f, float tol,
                                                    bool alive0, bool alive1, float *o) {
     const float2 cx = add2(PX, bc2(-f.catcher[0])), cy = add2(PY, bc2(-f.catcher[1])), cz = add2(PZ, bc2(-f.catcher[2]));
-    const bool c0 = (fabsf(cx.x) <= tol) & (fabsf(cy.x) <= tol) & (fabsf(cz.x) <= tol);
-    const bool c1 = (fabsf(cx.y) <= tol) & (fabsf(cy.y) <= tol) & (fabsf(cz.y) <= tol);
+    // inside the inclusive cube <=> the largest |component| is within the tolerance: one 3-input max
+    // (FMNMX3 with |x| operands) and one compare per objective instead of three chained compares
+    const bool c0 = fmaxf(fmaxf(fabsf(cx.x), fabsf(cy.x)), fabsf(cz.x)) <= tol;
+    const bool c1 = fmaxf(fmaxf(fabsf(cx.y), fabsf(cy.y)), fabsf(cz.y)) <= tol;
     if (WOBS) {
         const float2 dx = add2(PX, bc2(-f.anchor[0])), dy = add2(PY, bc2(-f.anchor[1])), dz = add2(PZ, bc2(-f.anchor[2]));
         const float2 h2 = fma2(dx, dx, mul2(dy, dy));
@@ -569,8 +570,9 @@ struct TileScalars {
 };
 
 template <int J, bool RAND>
-__device__ __forceinline__ void load_scalars(const StepParams &P, long long env, TileScalars<J> &s, uint64_t keep,
+__device__ __forceinline__ void load_scalars(const StepParams &P, int env32, TileScalars<J> &s, uint64_t keep,
                                              uint64_t stream) {
+    const size_t env = (size_t)env32;     // indices stay 32-bit in the kernel (n_envs < 2^31); one widening per address
     // goals[0] is never loaded: no sub-pose z depends on joint 0 (it turns about the world z axis), so
     // the register of a prefetched goals[0] would be dead on arrival, ptxas would hand it out as scratch
     // at once, and that write-after-write hazard parks the warp on the prefetch's full memory latency
@@ -585,7 +587,7 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, long long env,
         for (int i = 1; i < J; ++i) s.g[i] = ld_hint(P.goals + env * J + i, keep);
     }
     if (!RAND) {
-        if (env >= P.n) {
+        if (env32 >= (int)P.n) {
 #pragma unroll
             for (int i = 0; i < J; ++i) s.a[i] = 0.f;
         } else if (J == 4) {
@@ -655,23 +657,24 @@ step_kernel(const __grid_constant__ StepParams P) {
     // for the whole grid was measured earlier: ~37k same-address global atomics per launch serialise in L2;
     // a shared-memory atomic per tile costs nothing.)
     const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
-    auto tile_of = [&](int li) -> long long {
-        const long long t = P.tile_begin + (long long)li * gridDim.x + blockIdx.x;
-        return t < P.tile_end ? t : -1;
+    const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
+    auto tile_of = [&](int li) -> int {
+        const int t = tile_begin + li * (int)gridDim.x + (int)blockIdx.x;
+        return t < tile_end ? t : -1;
     };
-    auto grab_tile = [&]() -> long long {
+    auto grab_tile = [&]() -> int {
         int li = 0;
         if (lane == 0) li = atomicAdd(&queue_next, 1);
         return tile_of(__shfl_sync(0xffffffffu, li, 0));
     };
-    auto fetch_points = [&](long long tile, int b) {   // lane 0 only
+    auto fetch_points = [&](int tile, int b) {   // lane 0 only
         mbar_expect_tx(bar + b, tile_bytes);
-        bulk_load_hint(tile_buf(b), P.points + tile * kTile * rowlen, tile_bytes, bar + b, pol_stream);
+        bulk_load_hint(tile_buf(b), P.points + (size_t)tile * (size_t)(kTile * rowlen), tile_bytes, bar + b, pol_stream);
     };
 
     if (threadIdx.x == 0) queue_next = wpb;     // the first wpb tiles of the block go to its warps directly
     __syncthreads();
-    long long cur = tile_of(warp);
+    int cur = tile_of(warp);
 #ifdef MT_TRACE
     const unsigned long long trace_t0 = trace_now();
     unsigned trace_tiles = 0;
@@ -688,23 +691,24 @@ step_kernel(const __grid_constant__ StepParams P) {
     __syncwarp();
     TileScalars<J> sc;
     load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
-    long long nxt = grab_tile();
+    int nxt = grab_tile();
     int b = 0;
     uint32_t phase0 = 0, phase1 = 0;
     const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
     uint32_t ground_steps = 0;              // warp-uniform: ground-contact env-steps of this warp's tiles
 
     while (true) {
-        const long long env0 = cur * kTile, env = env0 + lane;
-        const bool full = env0 + kTile <= P.n;  // warp-uniform
-        const bool valid = env < P.n;
+        const int env0 = cur * kTile, env32 = env0 + lane;
+        const size_t env = (size_t)env32;
+        const bool full = env0 + kTile <= n_envs;  // warp-uniform
+        const bool valid = env32 < n_envs;
 
         // 1. next tile's scalars on their way to registers
         TileScalars<J> sn;
         if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
         // 2. kinematics of the current tile (needs no objectives)
-        if (RAND) draw_actions(P, P.env_id_base + env, J, sc.a);
+        if (RAND) draw_actions(P, P.env_id_base + env32, J, sc.a);
         Frames f;
         float jbuf[J * 3];
         float *jout = P.joints ? jbuf : nullptr;
@@ -761,17 +765,17 @@ step_kernel(const __grid_constant__ StepParams P) {
         while (pending) {
             const int src = __ffs(pending) - 1;
             pending &= pending - 1u;
-            const long long renv = env0 + src;
+            const size_t renv = (size_t)(env0 + src);
             const uint32_t ep = P.episode[renv];                           // resets so far (broadcast load)
             __syncwarp();
             if (lane == src) P.episode[renv] = ep + 1u;
             if (lane < x) {
                 float px, py, pz;
                 if (P.obj_stream) {
-                    const float *srcp = P.obj_stream + (((long long)(ep % (uint32_t)P.obj_sets) * P.n + renv) * x + lane) * 3;
+                    const float *srcp = P.obj_stream + (((size_t)(ep % (uint32_t)P.obj_sets) * (size_t)P.n + renv) * x + lane) * 3;
                     px = srcp[0]; py = srcp[1]; pz = srcp[2];
                 } else {
-                    sample_point(P, P.env_id_base + renv, ep, lane, px, py, pz);
+                    sample_point(P, P.env_id_base + (long long)renv, ep, lane, px, py, pz);
                 }
                 float *grow = P.points + renv * rowlen;
                 grow[point_index((x & 1) == 0, lane, 0)] = px;
@@ -812,7 +816,7 @@ step_kernel(const __grid_constant__ StepParams P) {
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_store_hint(P.obs + env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
+                    bulk_store_hint(P.obs + (size_t)env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
                     bulk_commit();
                 }
             } else if (valid) {
