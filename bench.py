@@ -189,7 +189,7 @@ def run_reference_arm(args) -> None:
             "cpu_baseline": {"value": value, "unit": METRIC, "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _RESULT_LINE.append(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------
@@ -384,10 +384,13 @@ def run_gpu(args) -> None:
             "modes": modes,
             "episode_stats": stats,
         }
-        print(json.dumps(line), flush=True)
+        _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_RESULT_LINE = []      # the one JSON line, printed by main() after stdout has been restored
 
 
 def main():
@@ -404,10 +407,22 @@ def main():
     ap.add_argument("--burn-in", type=int, default=HORIZON,
                     help="untimed random-action steps before warm-up so episodes reach their steady state")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-    else:
-        run_gpu(args)
+    # stdout carries exactly ONE line, the JSON result: anything a library writes to file descriptor 1 on the
+    # way (NCCL prints its version there when the box sets NCCL_DEBUG) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference_arm(args)
+        else:
+            run_gpu(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[-1], flush=True)
 
 
 if __name__ == "__main__":
