@@ -374,7 +374,11 @@ def run_gpu(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "mt::step_kernel<0,10,false,true>",
                          "algorithmic_bytes_per_env_step": B, "kernel_ms_per_launch": kernel_ms,
-                         "envs_per_launch": n},
+                         "envs_per_launch": n,
+                         # the algorithmic count includes the 48 B/env-step of per-env state that the kernel keeps in
+                         # L2 from launch to launch, so `frac` can pass 1; this is the DRAM side on its own
+                         "dram_achieved": (traffic / kernel_ms / 1e6) if traffic else None,
+                         "dram_frac": (traffic / kernel_ms / 1e6 / peak) if traffic else None},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers, 16 chunks over 4 streams)",

@@ -15,6 +15,7 @@ ap.add_argument("--arm", default="ref")
 ap.add_argument("--rounds", type=int, default=6)
 ap.add_argument("--steps", type=int, default=400)
 ap.add_argument("--modes", default="step,rand,noobs")
+ap.add_argument("--fk-mode", type=int, default=0)
 ap.add_argument("--isolate", type=int, default=0, metavar="REPS",
                 help="one PROCESS per library, REPS passes over the list (A B C A B C ...): handles that share a "
                      "process also share the L2, and the evict_last state lines of the idle ones stay resident")
@@ -23,7 +24,7 @@ args = ap.parse_args()
 if args.isolate:
     import re, subprocess
     base = [sys.executable, os.path.abspath(__file__), "--lg", str(args.lg), "--x", str(args.x), "--arm", args.arm,
-            "--rounds", str(args.rounds), "--steps", str(args.steps), "--modes", args.modes]
+            "--rounds", str(args.rounds), "--steps", str(args.steps), "--modes", args.modes, "--fk-mode", str(args.fk_mode)]
     acc = {}
     for rep in range(args.isolate):
         for lib in args.libs:
@@ -47,12 +48,12 @@ arm = UR5_ARM if args.arm == "ur5" else REFERENCE_ARM
 J = arm.n_joints
 envs = []
 for p, (_, keep) in zip(paths, specs):
-    for k in ("MT_L2_KEEP_MB", "MT_WARPS_PER_BLOCK"):
+    for k in ("MT_L2_KEEP_MB", "MT_WARPS_PER_BLOCK", "MT_POOL_PERCENT"):
         os.environ.pop(k, None)
     for kv in (keep.split(",") if keep else []):     # "48" = MT_L2_KEEP_MB=48; "K=V" sets any variable
         k, _, v = kv.rpartition("=")
         os.environ[k or "MT_L2_KEEP_MB"] = v
-    e = BatchedEnvs(n, args.x, arm=arm, device=0, auto_reset=True, horizon=1000, seed=1, lib_path=p)
+    e = BatchedEnvs(n, args.x, arm=arm, device=0, auto_reset=True, horizon=1000, seed=1, lib_path=p, fk_mode=args.fk_mode)
     e.reset()
     e.rollout_random(1000, write_obs=False)
     envs.append(e)
