@@ -9,8 +9,8 @@
 //   is_done       manytor.py:155-173
 //   reset         manytor.py:219-241   (auto-reset with on-device objective refresh)
 //
-// Mapping: persistent warps; one warp owns a tile of 32 consecutive envs at a time, one lane per
-// env.  The tile's objectives (3X fp32 per env, 120 B at X=10) are fetched from HBM by ONE TMA bulk
+// Mapping: one persistent block per SM; a warp owns a tile of 32 consecutive envs at a time, one lane
+// per env, and takes its next tile from the block's queue in shared memory.  The tile's objectives (3X fp32 per env, 120 B at X=10) are fetched from HBM by ONE TMA bulk
 // copy into shared memory while the lanes do the kinematics (which need no objectives);
 // observations are written in place over the objectives and leave by ONE TMA bulk store, so the
 // row-major [N][3X] layouts are moved with full-line transactions and no per-lane strided access.
@@ -609,10 +609,10 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
 //   X    objectives per env, 0 = run-time P.n_obj
 //   RAND draw actions in-kernel (mt_rollout_random)   WOBS write observations
 //
-// Persistent warps: the grid is sized to the SMs (blocks/SM from the occupancy
-// API) and every warp walks its round-robin share of the 32-env tiles, so all
-// SMs finish together.  Each warp software-pipelines its
-// tiles: while it computes tile i it has tile i+1's scalars in flight to
+// Persistent blocks: one per SM (as many warps as the SM holds; several smaller
+// blocks for launches with few tiles), each owning every G-th tile and handing
+// them to its warps from a queue in shared memory.  Each warp software-pipelines
+// its tiles: while it computes tile i it has tile i+1's scalars in flight to
 // registers (coalesced vector loads) and tile i+1's objectives in flight to its
 // second shared-memory buffer (TMA bulk copy + mbarrier), and tile i-1's
 // observations draining from the other buffer to HBM (TMA bulk store).
