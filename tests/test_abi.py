@@ -131,3 +131,22 @@ def test_plain_c_host_links_against_the_abi(lib, tmp_path):
         assert res.returncode == 0, res.stderr
     else:
         assert res.returncode == 1 and "no CPU fallback" in res.stderr
+
+
+def test_no_prefetch_register_is_overwritten_unread():
+    """Regression guard for the hazard that cost 21 % of the step kernel's stall samples: a register that
+    receives a tile-ahead prefetch (LDG) must not be written again before something has read it, or the
+    overwrite waits for the load and the prefetch becomes a blocking load (tools/sass_waw.py).  Checked
+    on the SASS of every reference-arm variant of the built library."""
+    import shutil
+    import subprocess
+    import sys
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from manytor_b200 import _lib
+    sass = subprocess.run([cuobjdump, "-sass", _lib.library_path()], capture_output=True, text=True, check=True).stdout
+    assert "step_kernelILi0ELi10ELb0ELb1" in sass, "headline kernel missing from the library"
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "sass_waw.py")
+    out = subprocess.run([sys.executable, tool, "step_kernelILi0E"], input=sass, capture_output=True, text=True, check=True).stdout
+    assert out.strip().endswith("0 suspicious prefetch overwrite(s)"), out

@@ -45,6 +45,11 @@ def dest_regs(text):
     return dst, src, op
 
 
+def complementary(a, b):
+    pa, pb = re.match(r"@(!?)(U?P\d+)\s", a), re.match(r"@(!?)(U?P\d+)\s", b)
+    return bool(pa and pb and pa.group(2) == pb.group(2) and pa.group(1) != pb.group(1))
+
+
 def main():
     want = sys.argv[1] if len(sys.argv) > 1 else ""
     kern, ins, bad = None, [], 0
@@ -62,6 +67,8 @@ def main():
                 if op2.split(".")[0] in ("BRA", "EXIT", "RET") and not text2.startswith("@"):
                     break                          # end of the straight-line region this load belongs to
                 pending -= s2                      # read: the scoreboard wait is a true dependency, fine
+                if complementary(text, text2):     # "@!P2 LDG" / "@P2 MOV": the two never both execute
+                    continue
                 hit = pending & d2
                 if hit:
                     print(f"{kern[:70]}: {text[:50]} @{addr}: R{sorted(hit)} overwritten unread by '{text2[:60]}' @{addr2}")
