@@ -11,9 +11,10 @@ objective refresh (BASELINE.json configs[2]: 4-joint arm, 2^20 envs per GPU, x=1
 (weak scaling, 2^20 per GPU, configs[3]); the only collective is one all-reduce of
 the episode statistics at the end of the timed region.
 
-`--impl reference` times the CPU restatement of the reference loop (oracle/, a
-vectorised numpy port pinned to the reference's golden traces; the reference
-itself is pure Python and cannot travel to the GPU box) on all host cores.
+`--impl reference` times the reference's own CPU implementation on all host cores:
+oracle/_ref (the unmodified reference, byte-compiled by oracle/make_ref.py in the
+build container; it travels to the GPU box with the snapshot) in a test_multi.py
+loop, or -- when that was never built -- the vectorised numpy port in oracle/.
 """
 from __future__ import annotations
 
@@ -128,10 +129,36 @@ def _oracle_worker_step(_):
     return int(r.reward.sum())
 
 
-def cpu_baseline_single_core(budget_s: float = 12.0) -> dict:
-    """Vectorised fp64 numpy oracle on ONE core, N=4096, x=10 ("host numpy" of the metric string),
-    plus the scalar per-env loop port (test_multi.py shape) as a second figure."""
+REF_SHAPE = (8, 8)        # Multienv((8,8), 10): SURVEY.md section 8(d)(i)
+
+
+def _ref_worker_init(seed):
+    """One process = the reference's own Multienv (oracle/_ref: the unmodified manytor.py, byte-compiled)."""
+    global _R
     import numpy as np
+    from oracle import make_ref
+    ref = make_ref.load()
+    np.random.seed(seed)
+    me = ref.Multienv(env_shape=REF_SHAPE, obj_number=OBJ)
+    me.reset()
+    _R = (me, [0])
+
+
+def _ref_worker_step(_):
+    me, count = _R
+    me.step(me.action_sample())                        # test_multi.py:20-21
+    count[0] += 1
+    if count[0] % 50 == 0:                             # test_multi.py:8,34: max_steps = 50, then reset()
+        me.reset()
+    return me.env_number
+
+
+def cpu_baseline_single_core(budget_s: float = 10.0) -> dict:
+    """The CPU figures the metric string asks for, on ONE core of this box:
+    (i) the unmodified reference's Multienv loop (oracle/_ref, test_multi.py shape) -- kind "reference";
+    (ii) the vectorised fp64 numpy oracle at N = 4096 ("host numpy") and the scalar loop port."""
+    import numpy as np
+    from oracle import make_ref
     n = 4096
     _oracle_worker_init(n, OBJ, 1)
     _oracle_worker_step(0)
@@ -140,34 +167,77 @@ def cpu_baseline_single_core(budget_s: float = 12.0) -> dict:
         _oracle_worker_step(0)
         steps += 1
     dt = time.perf_counter() - t0
-    from oracle.scalar_port import multienv_loop
-    t1 = time.perf_counter()
-    es, _ = multienv_loop(64, OBJ, 60, seed=0)       # Multienv((8,8), 10)-sized, ~4 s
-    dts = time.perf_counter() - t1
-    return {"value": n * steps / dt, "unit": METRIC, "cores": 1, "kind": "port",
-            "sample": f"oracle/manytor_oracle.py (vectorised fp64 numpy restatement of manytor.py:175-260), "
-                      f"{n} envs x {steps} steps, x={OBJ}, random integer actions, {dt:.1f}s on 1 core",
-            "scalar_loop_value": es / dts,
-            "scalar_loop_sample": f"oracle/scalar_port.py (per-env Python loop shaped like test_multi.py / "
-                                  f"manytor.py:115-122), 64 envs x 60 steps in {dts:.1f}s on 1 core"}
+    port = {"value": n * steps / dt, "sample": f"oracle/manytor_oracle.py (vectorised fp64 numpy restatement of manytor.py:175-260), "
+            f"{n} envs x {steps} steps, x={OBJ}, random integer actions, {dt:.1f}s on 1 core"}
+    out = None
+    if make_ref.load() is not None:
+        _ref_worker_init(0)
+        t1, rsteps = time.perf_counter(), 0
+        while time.perf_counter() - t1 < budget_s:
+            _ref_worker_step(0)
+            rsteps += 1
+        dtr = time.perf_counter() - t1
+        ne = REF_SHAPE[0] * REF_SHAPE[1]
+        out = {"value": ne * rsteps / dtr, "unit": METRIC, "cores": 1, "kind": "reference",
+               "sample": f"oracle/_ref (the unmodified reference, byte-compiled by oracle/make_ref.py): Multienv({REF_SHAPE}, {OBJ}), "
+                         f"reset() every 50 steps, {rsteps} x step(action_sample()) as in test_multi.py:11-34, no render, {dtr:.1f}s on 1 core",
+               "numpy_port_value": port["value"], "numpy_port_sample": port["sample"]}
+    else:
+        out = {"value": port["value"], "unit": METRIC, "cores": 1, "kind": "port", "sample": port["sample"],
+               "note": "oracle/_ref not present on this box: the reference itself was not timed"}
+    return out
+
+
+def config1_latency(steps: int = 1000) -> dict:
+    """BASELINE configs[0] through the drop-in: ONE env, x = 10, `steps` x step(action_sample()) via
+    manytor_b200.manytor.Environment (reset on done, test_single.py:17-21) -- a latency figure, not throughput."""
+    import manytor_b200.manytor as tor
+    env = tor.Environment(OBJ, seed=SEED)
+    env.reset()
+    for _ in range(20):
+        env.step(env.action_sample())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, done = env.step(env.action_sample())
+        if done:
+            env.reset()
+    dt = time.perf_counter() - t0
+    return {"workload": "configs[0]: Environment(10), 1000 x step(action_sample()), reset on done", "steps": steps,
+            "env_steps_per_s": steps / dt, "us_per_step": 1e6 * dt / steps,
+            "note": "each iteration = mt_sample_actions + D2H + mt_step + 3 D2H through ctypes/torch; launch-latency bound"}
 
 
 def run_reference_arm(args) -> None:
-    """`--impl reference`: the CPU port of the reference loop on all host cores."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores --
+    oracle/_ref (the unmodified reference) when it was built, else the numpy port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    from oracle import make_ref
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     procs = max(1, min(cores, 64))
-    n = 4096
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = "1"
     ctx = mp.get_context("fork")
-    pools = [ctx.Pool(1, initializer=_oracle_worker_init, initargs=(n, OBJ, 100 + i)) for i in range(procs)]
+    use_ref = make_ref.load() is not None and not args.reference_port
+    if use_ref:
+        per = REF_SHAPE[0] * REF_SHAPE[1]
+        pools = [ctx.Pool(1, initializer=_ref_worker_init, initargs=(100 + i,)) for i in range(procs)]
+        fn = _ref_worker_step
+        kind = "reference"
+        sample = (f"oracle/_ref (the unmodified reference, byte-compiled): {procs} processes x Multienv({REF_SHAPE}, {OBJ}) "
+                  f"x {args.steps} steps of step(action_sample()) (test_multi.py:11-34, no render)")
+    else:
+        per = 4096
+        pools = [ctx.Pool(1, initializer=_oracle_worker_init, initargs=(per, OBJ, 100 + i)) for i in range(procs)]
+        fn = _oracle_worker_step
+        kind = "port"
+        sample = (f"oracle/manytor_oracle.py (vectorised fp64 numpy port of the reference step, pinned to the "
+                  f"reference's golden traces), {procs} processes x {per} envs x {args.steps} steps, x={OBJ}")
 
     def step_all():
-        rs = [p.apply_async(_oracle_worker_step, (0,)) for p in pools]
+        rs = [p.apply_async(fn, (0,)) for p in pools]
         return [r.get() for r in rs]
 
     for _ in range(max(args.warmup, 1)):
@@ -178,15 +248,13 @@ def run_reference_arm(args) -> None:
     dt = time.perf_counter() - t0
     for p in pools:
         p.terminate()
-    value = procs * n * args.steps / dt
-    sample = (f"oracle/manytor_oracle.py (vectorised fp64 numpy port of the reference step, pinned to the "
-              f"reference's golden traces), {procs} processes x {n} envs x {args.steps} steps, x={OBJ}")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
+    value = procs * per * args.steps / dt
+    line = {"impl": "reference", "impl_class": "cpu", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU arm: each step = one env-step of a bounded sample "
-                       f"({procs} x {n} envs) of the workload"},
-            "cpu_baseline": {"value": value, "unit": METRIC, "cores": procs, "kind": "port", "sample": sample},
+                       f"({procs} x {per} envs) of the workload; throughput is per env-step, so the sample size does not enter the ratio"},
+            "cpu_baseline": {"value": value, "unit": METRIC, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _RESULT_LINE.append(json.dumps(line))
@@ -212,95 +280,149 @@ def run_gpu(args) -> None:
     cores = mtd.bind_to_gpu_numa(local) if world > 1 else None      # keep pinned buffers on the GPU's NUMA node
 
     n = ENVS_PER_GPU
-    base, _ = rank * n, n
+    base = rank * n
     env = BatchedEnvs(n, OBJ, device=local, env_id_base=base, horizon=HORIZON, auto_reset=True, seed=SEED)
     env.reset()
-    # burn-in to the steady state of the episode process (resets every ~550 steps per env)
-    env.rollout_random(args.burn_in, write_obs=False)
-    K, W = args.steps, max(args.warmup, 3)
+    K, W, R = args.steps, max(args.warmup, 3), max(args.repeats, 1)
+    stream = torch.cuda.current_stream(dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
-    n_act = min(K + W, 64)
-    actions = [torch.randint(-180, 180, (n, 4), device=dev, generator=gen).float() for _ in range(n_act)]
-    torch.cuda.synchronize()
+    # One action buffer per timed AND per warm-up step, refilled with fresh uniform integer degrees before
+    # every repeat: no env ever sees an action twice, i.e. the timed steps ARE a random-action rollout.
+    n_buf = min(K + W, 2048)
+    actions = [torch.empty((n, 4), device=dev, dtype=torch.float32) for _ in range(n_buf)]
+
+    def refill():
+        for a in actions:
+            a.copy_(torch.randint(-180, 180, (n, 4), device=dev, generator=gen))
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    stream = torch.cuda.current_stream(dev)
-
-    def timed(fn, k, w):
-        for i in range(w):
-            fn(i)
+    def fence():
         torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = env.launch_count
-        e0.record(stream)
-        for i in range(k):
-            fn(w + i)
-        e1.record(stream)
-        torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1), env.launch_count - l0
 
-    # ---- headline: K x mt_step, actions from HBM, obs written (309 B/env-step) ----------
-    sampler = ClockSampler(local, args.clock_period_ms) if rank == 0 and args.clock_period_ms > 0 else None
-    stats_holder = {}
+    # ---- steady state: clock warm-up + burn-in with in-kernel random actions (never cycled) -----------
+    env.clear_stats()
+    env.rollout_random(args.burn_in, write_obs=False)
+    t_warm = time.perf_counter()
+    while time.perf_counter() - t_warm < args.clock_warm_s:          # same kernel family, obs written: clocks/power settle
+        env.rollout_random(200, write_obs=True)
+        torch.cuda.synchronize()
+    refill()
+    torch.cuda.synchronize()
 
     def step_fn(i):
-        env.step(actions[i % n_act])
+        env.step(actions[i % n_buf])
 
-    # bring clocks / power state to steady load before timing (untimed, same kernel)
-    t_warm = time.perf_counter()
-    while time.perf_counter() - t_warm < args.clock_warm_s:
-        for i in range(200):
-            step_fn(i)
-        torch.cuda.synchronize()
-    # The K timed steps are K launches of the step kernel either way; by default they are submitted
-    # as ONE CUDA graph (captured untimed, each node its own action buffer), which is how an RL loop
-    # that graphs policy + env drives it and removes the ~3 us per-launch gap of stream launches.
-    graph = None
-    if not args.no_graph:
+    def capture(body):
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(stream)
             with torch.cuda.stream(side):
-                for i in range(3):
-                    step_fn(i)
+                body(True)
             stream.wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                for i in range(K):
-                    step_fn(W + i)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body(False)
+            return g
         except Exception as ex:
             print(f"bench: CUDA graph capture failed ({ex}); timing stream launches", file=sys.stderr)
-            graph = None
+            return None
+
+    # The K timed steps are K launches of the step kernel either way; by default they are submitted as ONE
+    # K-node CUDA graph (each node its own action buffer), which is how an RL loop that graphs policy + env
+    # drives it and removes the ~3 us per-launch gap of stream launches from Python.
+    graph = None if args.no_graph else capture(lambda warm: [step_fn(W + i) for i in range(3 if warm else K)])
+    sampler = ClockSampler(local, args.clock_period_ms) if rank == 0 and args.clock_period_ms > 0 else None
     if sampler:
         sampler.start()
+
+    def timed_region(replay, eager):
+        """W warm-up steps, then EXACTLY K steps + the end-of-rollout statistics all-reduce, on the device clock."""
+        for i in range(W):
+            step_fn(i)
+        fence()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        if replay is not None:
+            replay.replay()
+        else:
+            eager()
+        e1.record(stream)
+        st = env.stats_tensor()                       # end-of-rollout statistics ...
+        mtd.allreduce_stats(st)                       # ... one NCCL all-reduce (config 4)
+        e2.record(stream)
+        fence()
+        return e0.elapsed_time(e2), e0.elapsed_time(e1), st
+
+    if graph is not None:
+        graph.replay()                                # untimed: the first replay uploads the graph
+        torch.cuda.synchronize()
+    l0 = env.launch_count
+    reps = []
+    for r in range(R):
+        if r:
+            refill()                                  # fresh random actions for every repeat (untimed)
+        ms_all, ms_k, st = timed_region(graph, lambda: [step_fn(W + i) for i in range(K)])
+        reps.append((mtd.max_over_ranks(ms_all, dev), mtd.max_over_ranks(ms_k, dev)))
+    stats = mtd.stats_dict(st)                        # burn-in + warm-ups + every timed repeat, all ranks
+    launches_timed = (K + 1) if graph is not None else (env.launch_count - l0) // R - W
+    order = sorted(range(R), key=lambda i: reps[i][0])
+    med = order[(R - 1) // 2]                         # the (lower) median repeat IS the reported run
+    ms_total, ms_kernels = reps[med]
+    best_total = reps[order[0]][0]
+
+    # ---- SURVEY config-3 protocol: in-kernel RNG actions, same repeats ---------------------------------
+    def rand_mode(write_obs):
+        g = None if args.no_graph else capture(lambda warm: env.rollout_random(3 if warm else K, write_obs=write_obs))
+        if g is not None:
+            g.replay()
+        out = []
+        for r in range(R):
+            env.rollout_random(W, write_obs=write_obs)
+            fence()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if g is not None:
+                g.replay()
+            else:
+                env.rollout_random(K, write_obs=write_obs)
+            e1.record(stream)
+            fence()
+            out.append(mtd.max_over_ranks(e0.elapsed_time(e1), dev))
+        out.sort()
+        return out
+
+    peak, peak_src = peaks()
+
+    def mode_entry(times, bytes_per):
+        med_ms, best_ms = times[(len(times) - 1) // 2], times[0]
+        return {"env_steps_per_s": world * n * K / (med_ms * 1e-3), "best_env_steps_per_s": world * n * K / (best_ms * 1e-3),
+                "us_per_step_median": 1e3 * med_ms / K, "us_per_step_best": 1e3 * best_ms / K, "repeats": len(times),
+                "bytes_per_env_step": bytes_per, "hbm_gbs": n * K * bytes_per / (med_ms * 1e-3) / 1e9,
+                "frac_of_peak": n * K * bytes_per / (med_ms * 1e-3) / 1e9 / peak}
+
+    modes = {
+        "rollout_random_in_kernel_actions": mode_entry(rand_mode(True), env.bytes_per_env_step(False, True)),
+        "rollout_random_no_obs_write": mode_entry(rand_mode(False), env.bytes_per_env_step(False, False)),
+    }
+    # the same steps as individual stream launches from Python (no graph)
     for i in range(W):
         step_fn(i)
-    if graph is not None:
-        graph.replay()                            # untimed: first replay uploads the graph
-    torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    l0 = env.launch_count
+    fence()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    if graph is not None:
-        graph.replay()                            # exactly K steps
-    else:
-        for i in range(K):
-            step_fn(W + i)
+    for i in range(K):
+        step_fn(W + i)
     e1.record(stream)
-    st = env.stats_tensor()                       # end-of-rollout statistics ...
-    mtd.allreduce_stats(st)                       # ... one NCCL all-reduce (config 4)
-    e2.record(stream)
-    torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
-    # my kernels inside the timed region: K step kernels (graph nodes or stream launches) + 1 stats kernel
-    launches_timed = (K + 1) if graph is not None else env.launch_count - l0
-    timed_ms_local = e0.elapsed_time(e2)
-    # K steps last only a few ms, far below nvidia-smi's sampling period: keep the same step
-    # loop running (untimed) so the clock sampler sees the load the timed region ran under
+    fence()
+    modes["step_hbm_actions_stream_launches"] = mode_entry([mtd.max_over_ranks(e0.elapsed_time(e1), dev)], env.bytes_per_env_step(True, True))
+
+    # K steps last only a few ms, far below nvidia-smi's sampling period: keep the same load running
+    # (untimed) so the clock sampler sees what the timed regions ran under
     t_cont = time.perf_counter()
     while sampler and time.perf_counter() - t_cont < args.clock_probe_s:
         for i in range(200):
@@ -308,49 +430,44 @@ def run_gpu(args) -> None:
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
     if clocks is not None:
-        clocks["note"] = (f"sampled every {args.clock_period_ms} ms from just before the warm-up steps, through the {timed_ms_local:.1f} ms "
-                          f"timed region, and over a {args.clock_probe_s:.1f} s untimed continuation of the same step loop")
-    launches = launches_timed
-    ms_total = mtd.max_over_ranks(e0.elapsed_time(e2), dev)
-    ms_kernels = mtd.max_over_ranks(e0.elapsed_time(e1), dev)
-    stats = mtd.stats_dict(st)
+        clocks["note"] = (f"sampled every {args.clock_period_ms} ms from just before the first timed repeat, through the {R} timed "
+                          f"regions of {ms_total:.1f} ms and the other modes, and over a {args.clock_probe_s:.1f} s untimed continuation of the same step loop")
+
     value = world * n * K / (ms_total * 1e-3)
     B = env.bytes_per_env_step(True, True)
     kernel_ms = ms_kernels / K
-    peak, peak_src = peaks()
     achieved = B * n / (kernel_ms * 1e-3) / 1e9
 
-    # ---- other modes (short), for the roofline discussion -------------------------------
-    modes = {}
-    KM = min(K, 500)
-    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=True), KM, 3)
-    modes["rollout_random_in_kernel_actions"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, True)}
-    ms, _ = timed(lambda i: env.rollout_random(1, write_obs=False), KM, 3)
-    modes["rollout_random_no_obs_write"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": env.bytes_per_env_step(False, False)}
-    # the same steps as individual stream launches from Python (no graph)
-    ms, _ = timed(step_fn, KM, 3)
-    modes["step_hbm_actions_stream_launches"] = {"env_steps_per_s": n * KM / (ms * 1e-3), "bytes_per_env_step": B}
-    for m in modes.values():
-        if "error" in m:
-            continue
-        m["hbm_gbs"] = m["env_steps_per_s"] * m["bytes_per_env_step"] / 1e9
-        m["frac_of_peak"] = m["hbm_gbs"] / peak
-
     # ---- e2e: host buffers through the public API (H2D actions, D2H obs/reward/done) ----
-    act_pinned = env.pinned("actions", (n, 4), np.float32)
-    act_pinned[:] = np.random.RandomState(rank).randint(-180, 180, size=(n, 4)).astype(np.float32)
+    rs = np.random.RandomState(rank)
     e2e_steps = max(3, min(K, 10))
-    for _ in range(2):
-        env.step_host(act_pinned)
+    e2e_acts = []                                           # one page-locked action buffer per timed step: fresh random actions
+    for i in range(e2e_steps):
+        a = env.pinned(f"actions{i}", (n, 4), np.float32)
+        a[:] = rs.randint(-180, 180, size=(n, 4))
+        e2e_acts.append(a)
+    for i in range(2):
+        env.step_host(e2e_acts[i])
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        obs_h, rew_h, done_h = env.step_host(act_pinned)      # synchronous: results are in host memory
+    for i in range(e2e_steps):
+        obs_h, rew_h, done_h = env.step_host(e2e_acts[i])     # synchronous: results are in host memory
     torch.cuda.synchronize(); barrier()
     e2e_s = mtd.max_over_ranks(time.perf_counter() - t0, dev)
     e2e_value = world * n * e2e_steps / e2e_s
     h2d = n * 4 * 4
     d2h = n * (3 * OBJ * 4 + 4 + 1)
+    # what the link can carry: the same bytes as bare pinned-memory copies, all ranks at once
+    d_buf = torch.empty(d2h, dtype=torch.uint8, device=dev)
+    h_buf = torch.empty(d2h, dtype=torch.uint8).pin_memory()
+    h_buf.copy_(d_buf, non_blocking=True)
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        h_buf.copy_(d_buf, non_blocking=True)
+    torch.cuda.synchronize(); barrier()
+    d2h_s = mtd.max_over_ranks(time.perf_counter() - t0, dev) / 5
+    ceiling = world * n / d2h_s                                 # env-steps/s if a step were ONLY its D2H read-back
 
     if rank == 0:
         traffic = None
@@ -361,18 +478,28 @@ def run_gpu(args) -> None:
             except Exception:
                 traffic = None
         cpu = cpu_baseline_single_core() if world == 1 and not args.no_cpu else None
+        cfg1 = config1_latency() if world == 1 and not args.no_cpu else None
+        eps = max(stats["episodes"], 1)
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": n, "n_joints": 4, "n_obj": OBJ, "horizon": HORIZON,
-                       "terminate_on_ground": False, "auto_reset": True, "actions": "uniform integer degrees in [-180,180), read from HBM [N][4] fp32",
+                       "terminate_on_ground": False, "auto_reset": True,
+                       "actions": f"uniform integer degrees in [-180,180), read from HBM [N][4] fp32; {n_buf} distinct buffers "
+                                  "(one per warm-up and timed step), refilled before every repeat: no action is ever replayed",
                        "submission": "one K-node CUDA graph" if graph is not None else "K stream launches",
-                       "burn_in_steps": args.burn_in,
+                       "burn_in": f"{args.burn_in} + {args.clock_warm_s:.1f} s of in-kernel random-action steps before the first repeat (steady state of the episode process)",
+                       "repeats": f"{R} timed regions of exactly K steps each (W warm-up steps before each); value = the median region, best reported beside it",
                        "l2": f"working set {(n * (B + 8 * 4)) / 2**20:.0f} MiB per step > 126 MiB L2 (inputs larger than L2, no flush needed)",
-                       "parallelism": f"env-sharded x{world}, no per-step collective, 1 stats all-reduce"},
+                       "parallelism": f"env-sharded x{world}, no per-step collective, 1 stats all-reduce (inside the timed region: "
+                                      "a 148-block stats kernel + one ncclAllReduce of 64 B, the only thing that grows with N)"},
+            "repeats": {"n": R, "ms_per_step_all": [t / K for t, _ in reps], "median_ms_per_step": ms_total / K,
+                        "best_ms_per_step": best_total / K, "best_value": world * n * K / (best_total * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "mt::step_kernel<0,10,false,true>",
+                         "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, committed in profiles/traffic.json (a constant of the kernel, NOT measured in this run)",
+                         "peak_source": peak_src, "kernel": "mt::step_kernel<0,10,false,true>",
                          "algorithmic_bytes_per_env_step": B, "kernel_ms_per_launch": kernel_ms,
                          "envs_per_launch": n,
                          # the algorithmic count includes the 48 B/env-step of per-env state that the kernel keeps in
@@ -382,11 +509,18 @@ def run_gpu(args) -> None:
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers, 16 chunks over 4 streams)",
-                    "cpu_binding": f"{len(cores)} cores next to the GPU (NVML affinity)" if cores else "none"},
-            "gpu_launches": launches,
+                    "cpu_binding": f"{len(cores)} cores next to the GPU (NVML affinity)" if cores else "none",
+                    "d2h_only_ceiling": ceiling, "frac_of_d2h_ceiling": e2e_value / ceiling,
+                    "ceiling_note": f"bare pinned D2H of the same {d2h} B per step on all {world} ranks at once: "
+                                    f"{d2h / d2h_s / 1e9:.1f} GB/s per GPU"},
+            "gpu_launches": launches_timed,
             "clocks": clocks,
             "modes": modes,
-            "episode_stats": stats,
+            "config1_single_env": cfg1,
+            "episode_stats": dict(stats, window="burn-in + warm-ups + all timed repeats (statistics cleared after reset)",
+                                  terminated_fraction=stats["terminated"] / eps, catches_per_episode=stats["catches"] / eps,
+                                  mean_episode_length=stats["length_sum"] / eps,
+                                  ground_rate=stats["ground_steps"] / max(stats["env_steps"], 1)),
         }
         _RESULT_LINE.append(json.dumps(line))
     if world > 1:
@@ -408,6 +542,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time K stream launches instead of one K-node CUDA graph")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--repeats", type=int, default=10, help="timed regions of K steps each; value = median, best beside it")
+    ap.add_argument("--reference-port", action="store_true", help="--impl reference: time the numpy port even when oracle/_ref exists")
     ap.add_argument("--burn-in", type=int, default=HORIZON,
                     help="untimed random-action steps before warm-up so episodes reach their steady state")
     args = ap.parse_args()

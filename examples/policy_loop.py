@@ -31,12 +31,15 @@ def main():
     def iteration():
         with torch.no_grad():
             torch.mul(policy(obs * (1.0 / 90.0)), 180.0, out=actions)     # joint targets in degrees
-        o, r, term, trunc, _ = env.step(actions)                          # o is the same buffer as `obs`
+        o, r, term, trunc, _ = env.step(actions)                          # o IS `obs`: reset() and step() return the same storage
         ret.add_(r)
         return o
 
+    first = obs.clone()
     for _ in range(5):
-        iteration()
+        o = iteration()
+    assert o.data_ptr() == obs.data_ptr(), "reset() and step() must hand out the same observation buffer"
+    assert not torch.equal(first, obs), "the policy input did not change between iterations"
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define MT_ABI_VERSION 1
+#define MT_ABI_VERSION 2
 #define MT_MAX_JOINTS 8
 #define MT_MAX_OBJ 32
 
@@ -112,12 +112,25 @@ int mt_config_init(mt_config *cfg);
 int mt_create(const mt_config *cfg, mt_env **out);
 int mt_destroy(mt_env *env);
 int mt_get_config(const mt_env *env, mt_config *out);
-/* Re-key the on-device Philox streams (actions, objective refresh); takes effect from the next
- * launch.  Gym-style reset(seed=...). */
+/* Re-seed the on-device Philox streams (actions, objective refresh): new key AND the counters that
+ * index the streams (per-env episode count, step index) back to zero, so reset(seed=s) reproduces the
+ * same objectives and actions every time it is called with the same s (Gymnasium's reset(seed=...)
+ * contract).  Synchronous (waits for the device). */
 int mt_set_seed(mt_env *env, uint64_t seed);
 
+/* The step index that keys the action stream of mt_sample_actions / mt_rollout_random.  It lives in
+ * DEVICE memory and is advanced by the step kernel itself (the last block of every mt_step,
+ * mt_step_host and of each step of mt_rollout_random), as are mt_stats.env_steps and the other
+ * statistics.  Consequence for CUDA graphs: a captured mt_step / mt_rollout_random can be replayed
+ * any number of times -- every replay counts its env-steps and draws fresh actions, exactly like the
+ * same calls issued eagerly.  Get/set are synchronous 8-byte copies (checkpoint / resume). */
+int mt_get_step_index(mt_env *env, uint64_t *out);
+int mt_set_step_index(mt_env *env, uint64_t value);
+
 /* Environment.reset / Multienv.reset -- manytor.py:219-253, 106-109.
- * mask_dev: NULL = all envs, else [N] uint8 selecting the envs to reset.
+ * mask_dev: NULL = all envs, else [N] uint8 selecting the envs to reset.  The FIRST reset of a handle
+ * must cover every env (NULL or an all-ones mask; a partial first mask returns MT_ERR_STATE after one
+ * small synchronous check): the reference raises IndexError when a never-reset env is stepped.
  * Fresh objectives come from the objective stream if one is set, else from the
  * on-device half-ball sampler (uniform in {|p|<=radius, z>=0}). */
 int mt_reset(mt_env *env, const uint8_t *mask_dev, void *stream);
@@ -138,13 +151,17 @@ int mt_sample_actions(mt_env *env, float *actions_dev, void *stream);
 
 /* n_steps x step(action_sample()) with the actions drawn inside the step kernel
  * (same stream of actions as mt_sample_actions).  obs_dev/reward_dev/done_dev are
- * overwritten every step; obs_dev may be NULL to skip the observation write. */
+ * overwritten every step; obs_dev may be NULL to skip the observation write;
+ * reward_dev / done_dev may be NULL, the results then go to buffers the handle owns
+ * (a host without CUDA headers can drive a rollout and read only the statistics). */
 int mt_rollout_random(mt_env *env, int32_t n_steps, float *obs_dev, float *reward_dev,
                       uint8_t *done_dev, void *stream);
 
 /* Host-buffer step: actions_host/obs_host/reward_host/done_host must be pinned
  * (mt_host_alloc).  Copies actions H2D, steps, copies results D2H, chunked over
- * internal streams so copies overlap the kernel; synchronous on return. */
+ * internal streams so copies overlap the kernels; synchronous on return.  Ordered after
+ * everything submitted earlier to the legacy default stream / blocking streams (work on
+ * cudaStreamNonBlocking streams must be synchronised by the caller). */
 int mt_step_host(mt_env *env, const float *actions_host, float *obs_host, float *reward_host,
                  uint8_t *done_host);
 int mt_host_alloc(void **out, uint64_t bytes);
@@ -164,7 +181,9 @@ int mt_get_state(mt_env *env, float *goals_dev, uint32_t *alive_dev, float *tota
  * The e-th reset of env n takes set (e mod n_sets).  NULL/0 restores the sampler. */
 int mt_set_objective_stream(mt_env *env, const float *points_dev, int32_t n_sets);
 
-/* One-env copy-back for the render shim (manytor.py:196-201).  Synchronous. */
+/* One-env copy-back for the render shim and per-env attribute reads (manytor.py:131-139,
+ * 196-201).  Synchronous, on the legacy default stream: one small kernel + one copy through
+ * scratch buffers the handle owns (no allocation, no device-wide synchronisation). */
 int mt_fetch_env(mt_env *env, int64_t index, float *goals_host, float *joints_host,
                  float *points_host, uint32_t *alive_host, float *total_reward_host);
 
@@ -173,6 +192,17 @@ int mt_fetch_env(mt_env *env, int64_t index, float *goals_host, float *joints_ho
 int mt_stats_device(mt_env *env, int64_t *stats_dev, void *stream);
 int mt_stats_host(mt_env *env, mt_stats *out);
 int mt_stats_clear(mt_env *env, void *stream);
+
+/* The ONE collective of a multi-GPU rollout: every shard's statistics summed
+ * with ncclAllReduce (NVLink / NVSwitch).  NCCL is dlopen'ed at first use (libnccl.so.2).
+ *   mt_stats_allreduce       one process driving n handles on n distinct devices; communicators
+ *                            from ncclCommInitAll, cached per device list.  Synchronous; the sum
+ *                            over all handles is written to *out_host.
+ *   mt_stats_allreduce_comm  one process per GPU: `nccl_comm` is the caller's ncclComm_t
+ *                            (ncclCommInitRank); stats_dev [MT_STATS_WORDS] int64 on the handle's
+ *                            device receives the global sum, asynchronously on `stream`. */
+int mt_stats_allreduce(mt_env *const *envs, int32_t n, mt_stats *out_host);
+int mt_stats_allreduce_comm(mt_env *env, void *nccl_comm, int64_t *stats_dev, void *stream);
 
 /* Module-level helpers of the reference, batched over M rows:
  * fk(mode, goals) manytor.py:35-53 -> out [M][16]; dh(a, alfa, d, theta) :25-32 ->

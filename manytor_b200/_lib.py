@@ -13,7 +13,7 @@ from . import build as _build
 MT_MAX_JOINTS = 8
 MT_MAX_OBJ = 32
 MT_STATS_WORDS = 8
-MT_ABI_VERSION = 1
+MT_ABI_VERSION = 2
 
 STATS_FIELDS = ("env_steps", "episodes", "terminated", "reward_sum", "length_sum", "catches",
                 "ground_steps", "live_reward_sum")
@@ -64,6 +64,8 @@ SIGNATURES = {
     "mt_destroy": (C.c_int, [_P]),
     "mt_get_config": (C.c_int, [_P, C.POINTER(MtConfig)]),
     "mt_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "mt_get_step_index": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "mt_set_step_index": (C.c_int, [_P, C.c_uint64]),
     "mt_reset": (C.c_int, [_P, _P, _P]),
     "mt_observe": (C.c_int, [_P, _P, _P]),
     "mt_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
@@ -81,6 +83,8 @@ SIGNATURES = {
     "mt_stats_device": (C.c_int, [_P, _P, _P]),
     "mt_stats_host": (C.c_int, [_P, C.POINTER(MtStats)]),
     "mt_stats_clear": (C.c_int, [_P, _P]),
+    "mt_stats_allreduce": (C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(MtStats)]),
+    "mt_stats_allreduce_comm": (C.c_int, [_P, _P, _P, _P]),
     "mt_fk": (C.c_int, [C.POINTER(MtConfig), C.c_int32, _P, _P, C.c_int64, _P]),
     "mt_dh": (C.c_int, [_P, _P, C.c_int64, _P]),
     "mt_joints": (C.c_int, [_P, _P, _P, C.c_int64, _P]),

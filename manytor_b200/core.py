@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -93,30 +94,39 @@ def _device_index(device) -> int:
     return d.index if d.index is not None else torch.cuda.current_device()
 
 
+class _PinnedBlock:
+    """Owner of one page-locked allocation (mt_host_alloc).  The numpy views handed to callers keep
+    it alive through their base chain (view -> ctypes buffer -> block), so the memory is released
+    only when the last view is gone -- not when the BatchedEnvs that allocated it is collected."""
+
+    def __init__(self, nbytes: int, alloc=None, free=None):
+        lib = _lib.load() if alloc is None else None
+        self._free = free if free is not None else lib.mt_host_free
+        ptr = C.c_void_p()
+        if alloc is None:
+            _lib.check(lib.mt_host_alloc(C.byref(ptr), max(int(nbytes), 1)))
+        else:
+            ptr = C.c_void_p(alloc(max(int(nbytes), 1)))
+        self.ptr = ptr.value
+        self._finalizer = weakref.finalize(self, self._free, C.c_void_p(self.ptr))
+
+
 class PinnedArray:
     """A numpy array over page-locked host memory (mt_host_alloc)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, alloc=None, free=None):
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
-        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
-        self._ptr = C.c_void_p()
-        _lib.check(_lib.load().mt_host_alloc(C.byref(self._ptr), max(nbytes, 1)))
-        buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
-        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+        count = int(np.prod(self.shape))
+        nbytes = count * self.dtype.itemsize
+        self.block = _PinnedBlock(nbytes, alloc, free)
+        buf = (C.c_char * max(nbytes, 1)).from_address(self.block.ptr)
+        buf._mt_block = self.block                     # the buffer object is the base of every view below
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=count).reshape(self.shape)
 
     @property
     def ptr(self) -> int:
-        return self._ptr.value
-
-    def __del__(self):
-        try:
-            if self._ptr:
-                self.array = None
-                _lib.load().mt_host_free(self._ptr)
-                self._ptr = None
-        except Exception:
-            pass
+        return self.block.ptr
 
 
 class BatchedEnvs:
@@ -190,7 +200,10 @@ class BatchedEnvs:
         m = self._mask(mask)
         _lib.check(self._lib.mt_reset(self._h, self._p(m), self._stream()))
         if returnable:
-            return self.observe()
+            # the same storage `step` writes its observations to: a policy that holds on to the tensor
+            # returned here keeps seeing fresh observations (examples/policy_loop.py)
+            self._out_buffers()
+            return self.observe(out=self._obs)
         return None
 
     def observe(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -242,9 +255,14 @@ class BatchedEnvs:
     def step_host(self, actions_host: np.ndarray, write_obs: bool = True):
         """Step with HOST buffers: H2D(actions) + kernel + D2H(obs, reward, done), chunked
         and overlapped on internal streams.  `actions_host` should come from
-        `pinned('actions', (N, J), float32)`; pageable input is staged through it."""
-        act = self.pinned("actions", (self.n, self.j), np.float32)
-        if actions_host is not act:
+        `pinned(name, (N, J), float32)` (any name: several buffers can be cycled); other
+        input is staged through `pinned('actions', ...)`.  The returned arrays are views of
+        page-locked buffers that the NEXT step_host overwrites; they stay valid (they own the
+        allocation) even after this object is gone."""
+        if any(actions_host is pa.array for pa in self._pinned.values()):
+            act = actions_host                             # already one of this object's page-locked buffers
+        else:
+            act = self.pinned("actions", (self.n, self.j), np.float32)
             np.copyto(act, np.asarray(actions_host, dtype=np.float32).reshape(self.n, self.j))
         obs = self.pinned("obs", (self.n, 3 * self.x), np.float32) if write_obs else None
         rew = self.pinned("reward", (self.n,), np.float32)
@@ -330,9 +348,23 @@ class BatchedEnvs:
                     total_reward=float(total.value))
 
     def set_seed(self, seed: int):
-        """Re-key the on-device action / objective streams (gym-style reset(seed=...))."""
+        """Re-seed the on-device action / objective streams (gym-style reset(seed=...)): new Philox key,
+        per-env episode counters and the step index back to zero, so the same seed reproduces the same
+        objectives and actions on the same handle."""
         _lib.check(self._lib.mt_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
         self.cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+
+    @property
+    def step_index(self) -> int:
+        """Steps executed so far; keys the action stream.  Lives on the device (advanced by the step
+        kernel, so CUDA-graph replays count); reading it synchronises."""
+        v = C.c_uint64()
+        _lib.check(self._lib.mt_get_step_index(self._h, C.byref(v)))
+        return int(v.value)
+
+    @step_index.setter
+    def step_index(self, value: int):
+        _lib.check(self._lib.mt_set_step_index(self._h, int(value) & 0xFFFFFFFFFFFFFFFF))
 
     # -- statistics ---------------------------------------------------------------
     def stats_tensor(self) -> torch.Tensor:

@@ -7,9 +7,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <unordered_map>
 #include <utility>
+#include <vector>
 
 #include "mt_jit.cuh"
 #include "mt_step.cuh"
@@ -53,6 +56,9 @@ struct DeviceGuard {
 // ----------------------------------------------------------------------------
 // handle
 // ----------------------------------------------------------------------------
+// mt_fetch_env scratch: goals[J] | joints[J][3] | points[X][3] | alive | total_reward
+constexpr int kFetchFloats = MT_MAX_JOINTS * 4 + MT_MAX_OBJ * 3 + 2;
+
 struct mt_env {
     mt_config cfg;
     long long n, n_pad, n_tiles;
@@ -65,7 +71,8 @@ struct mt_env {
     cudaKernel_t jit_kernel[2][2] = {};
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
-    unsigned long long *stats = nullptr;
+    unsigned long long *stats = nullptr;   // MT_STATS_WORDS: env_steps, finished-episode sums, ground steps (device side)
+    unsigned long long *ctrl = nullptr;    // kCtrlWords: step index + launch tickets (mt_step.cuh)
     float keep_fraction = 1.f; // share of the state lines marked evict_last (StepParams::pol_state)
     int32_t ep_shift = 0;      // > 0: ep_len packed into the alive word above bit ep_shift
     uint32_t ep_max = 65535u;
@@ -74,13 +81,19 @@ struct mt_env {
     std::unordered_map<unsigned long long, int> occupancy;   // (variant, warps per block) -> blocks per SM
     const float *obj_stream = nullptr;
     int32_t obj_sets = 0;
-    unsigned long long step_index = 0;
-    long long env_steps = 0, launches = 0;
+    long long launches = 0;
     bool was_reset = false;
+    // mt_fetch_env scratch (device + pinned host), mt_stats_host / mt_stats_allreduce buffers
+    float *scratch_reward = nullptr;       // mt_rollout_random with reward_dev / done_dev = NULL
+    uint8_t *scratch_done = nullptr;
+    float *fetch_dev = nullptr, *fetch_host = nullptr;
+    int64_t *stats_dev = nullptr, *stats_pin = nullptr;
     StepParams base;
     // mt_step_host resources
     static constexpr int kStreams = 4;
     cudaStream_t hs[kStreams] = {};
+    cudaEvent_t hev[kStreams + 1] = {};       // per stream "kernels done"; [kStreams] = entry fence
+    bool zero_copy = false;
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t *h_done = nullptr;
     // timing
@@ -287,8 +300,17 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     if (!e->ep_shift) ALLOC(e->counters, np * 4);
     ALLOC(e->episode, np * 4);
     ALLOC(e->points, np * X * 3 * 4);
-    ALLOC(e->stats, (MT_STATS_WORDS + kGroundSlots) * 8);
+    ALLOC(e->stats, MT_STATS_WORDS * 8);
+    ALLOC(e->ctrl, kCtrlWords * 8);
+    ALLOC(e->fetch_dev, kFetchFloats * 4);
+    ALLOC(e->stats_dev, MT_STATS_WORDS * 8);
 #undef ALLOC
+    if (cudaHostAlloc((void **)&e->fetch_host, kFetchFloats * 4, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&e->stats_pin, MT_STATS_WORDS * 8, cudaHostAllocDefault) != cudaSuccess) {
+        int rc = fail(MT_ERR_CUDA, "cudaHostAlloc of the handle's scratch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mt_destroy(e);
+        return rc;
+    }
     e->num_sms = prop.multiProcessorCount;
     fill_params(*cfg, e->base);
     e->base.goals = e->goals;
@@ -298,6 +320,7 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
     e->base.episode = e->episode;
     e->base.points = e->points;
     e->base.stats = e->stats;
+    e->base.ctrl = e->ctrl;
     e->base.n = e->n;
     e->base.tile_begin = 0;
     e->base.tile_end = e->n_tiles;
@@ -360,20 +383,50 @@ extern "C" int mt_destroy(mt_env *e) {
     DeviceGuard guard(e->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(e->goals); cudaFree(e->alive); cudaFree(e->total_reward); cudaFree(e->counters);
-    cudaFree(e->episode); cudaFree(e->points); cudaFree(e->stats);
+    cudaFree(e->episode); cudaFree(e->points); cudaFree(e->stats); cudaFree(e->ctrl);
+    cudaFree(e->fetch_dev); cudaFree(e->stats_dev); cudaFree(e->scratch_reward); cudaFree(e->scratch_done);
+    if (e->fetch_host) cudaFreeHost(e->fetch_host);
+    if (e->stats_pin) cudaFreeHost(e->stats_pin);
     cudaFree(e->h_actions); cudaFree(e->h_obs); cudaFree(e->h_reward); cudaFree(e->h_done);
     for (auto &s : e->hs) if (s) cudaStreamDestroy(s);
+    for (auto &v : e->hev) if (v) cudaEventDestroy(v);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     delete e;
     return MT_OK;
 }
 
+// Re-seeding restarts the on-device streams: the Philox key changes AND the counters that index the
+// streams (per-env episode count, step index) go back to zero, so reset(seed=s) reproduces the same
+// objectives and actions whenever it is called with the same s (Gymnasium's contract).  Synchronous.
 extern "C" int mt_set_seed(mt_env *e, uint64_t seed) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(e->episode, 0, (size_t)e->n_pad * 4));
+    CU(cudaMemset(e->ctrl + kCtrlStep, 0, 8));
+    CU(cudaDeviceSynchronize());
     e->cfg.seed = seed;
     e->base.seed_lo = (uint32_t)seed;
     e->base.seed_hi = (uint32_t)(seed >> 32);
+    return MT_OK;
+}
+
+// The step index that keys the action stream (mt_sample_actions / mt_rollout_random): part of a
+// checkpoint next to mt_get_state.  Synchronous (one 8-byte copy on the legacy default stream).
+extern "C" int mt_get_step_index(mt_env *e, uint64_t *out) {
+    if (!e || !out) return fail(MT_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(e->cfg.device);
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, e->ctrl + kCtrlStep, 8, cudaMemcpyDeviceToHost));
+    *out = v;
+    return MT_OK;
+}
+extern "C" int mt_set_step_index(mt_env *e, uint64_t value) {
+    if (!e) return fail(MT_ERR_INVALID, "env is NULL");
+    DeviceGuard guard(e->cfg.device);
+    const unsigned long long v = value;
+    CU(cudaMemcpy(e->ctrl + kCtrlStep, &v, 8, cudaMemcpyHostToDevice));
     return MT_OK;
 }
 
@@ -510,13 +563,13 @@ __global__ void sample_actions_kernel(const __grid_constant__ StepParams P, floa
     const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= P.n) return;
     float a[MT_MAX_JOINTS];
-    draw_actions(P, P.env_id_base + env, P.n_joints, a);
+    draw_actions(P, ld_volatile_u64(P.ctrl + kCtrlStep), P.env_id_base + env, P.n_joints, a);
     for (int i = 0; i < P.n_joints; ++i) actions[env * P.n_joints + i] = a[i];
 }
 
-// stats: finished-episode counters + a block/warp-shuffle reduction of the
-// in-progress total_reward, written as MT_STATS_WORDS int64.
-__global__ void stats_kernel(const __grid_constant__ StepParams P, long long env_steps, long long *out) {
+// stats: the device-side counters (env-steps, finished-episode sums, ground-contact steps) + a
+// block/warp-shuffle reduction of the in-progress total_reward, written as MT_STATS_WORDS int64.
+__global__ void stats_kernel(const __grid_constant__ StepParams P, long long *out) {
     long long local = 0;
     for (long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x; env < P.n;
          env += (long long)gridDim.x * blockDim.x)
@@ -531,17 +584,9 @@ __global__ void stats_kernel(const __grid_constant__ StepParams P, long long env
         local = (lane < (int)(blockDim.x >> 5)) ? part[lane] : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if (lane == 0) atomicAdd((unsigned long long *)(out + 7), (unsigned long long)local);
+        if (lane == 0 && local) atomicAdd((unsigned long long *)(out + 7), (unsigned long long)local);
     }
-    if (blockIdx.x == 0 && threadIdx.x < 6)
-        out[threadIdx.x] = threadIdx.x == 0 ? env_steps : (long long)P.stats[threadIdx.x];
-    if (blockIdx.x == 0 && warp == 1) {          // ground-contact steps: the per-warp slots of the step kernel
-        long long g = 0;
-        for (int i = lane; i < kGroundSlots; i += 32) g += (long long)P.stats[MT_STATS_WORDS + i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
-        if (lane == 0) out[6] = g + (long long)P.stats[6];
-    }
+    if (blockIdx.x == 0 && threadIdx.x < 7) out[threadIdx.x] = (long long)P.stats[threadIdx.x];
 }
 
 __global__ void fk_kernel(const __grid_constant__ StepParams P, int mode, const float *goals, long long m, float *out) {
@@ -638,7 +683,7 @@ static int check_ptr(const void *p, const char *name, bool required) {
 
 // launch the fused step kernel over tiles [t0, t1): a persistent grid sized to the SMs
 static int launch_step(mt_env *e, const float *actions, float *obs, float *reward, uint8_t *done, float *joints,
-                       bool rnd, long long t0, long long t1, cudaStream_t st) {
+                       bool rnd, long long t0, long long t1, cudaStream_t st, int ticket_slot = 0, bool advance = true) {
     StepParams P = e->base;
     P.actions = actions;
     P.obs = obs;
@@ -647,10 +692,12 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     P.joints = joints;
     P.obj_stream = e->obj_stream;
     P.obj_sets = e->obj_sets;
-    P.step_lo = (uint32_t)e->step_index;
-    P.step_hi = (uint32_t)(e->step_index >> 32);
     P.tile_begin = t0;
     P.tile_end = t1;
+    // device-side bookkeeping done by the launch's last block (mt_step.cuh, epilogue)
+    P.ticket_slot = ticket_slot;
+    P.advance = advance ? 1 : 0;
+    P.launch_envs = ((t1 * kTile < e->n) ? t1 * kTile : e->n) - t0 * kTile;
     const bool wobs = obs != nullptr;
     const void *fn = nullptr;
     if (e->jit) {
@@ -730,13 +777,28 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
 
 static inline unsigned blocks_for(long long n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
+__global__ void mask_gap_kernel(const uint8_t *mask, long long n, int64_t *flag) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env < n && !mask[env]) *flag = 1;
+}
+
 extern "C" int mt_reset(mt_env *e, const uint8_t *mask_dev, void *stream) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
     DeviceGuard guard(e->cfg.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mask_dev && !e->was_reset) {
+        // The reference raises IndexError when an env that was never reset is stepped (manytor.py:143);
+        // here the first reset has to cover every env, so that no env can be stepped with empty state.
+        CU(cudaMemsetAsync(e->stats_dev, 0, 8, st));
+        mask_gap_kernel<<<blocks_for(e->n), 256, 0, st>>>(mask_dev, e->n, e->stats_dev);
+        CU(cudaMemcpyAsync(e->stats_pin, e->stats_dev, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (e->stats_pin[0]) return fail(MT_ERR_STATE, "the first mt_reset must cover every env (mask leaves some env un-reset; the reference raises IndexError when such an env is stepped, manytor.py:143)");
+    }
     StepParams P = e->base;
     P.obj_stream = e->obj_stream;
     P.obj_sets = e->obj_sets;
-    reset_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(P, mask_dev);
+    reset_kernel<<<blocks_for(e->n), 256, 0, st>>>(P, mask_dev);
     CU(cudaGetLastError());
     e->launches++;
     e->was_reset = true;
@@ -779,20 +841,14 @@ extern "C" int mt_step(mt_env *e, const float *actions_dev, float *obs_dev, floa
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = timing_begin(e, st))) return rc;
     if ((rc = launch_step(e, actions_dev, obs_dev, reward_dev, done_dev, joints_dev, false, 0, e->n_tiles, st))) return rc;
-    if ((rc = timing_end(e, st))) return rc;
-    e->step_index++;
-    e->env_steps += e->n;
-    return MT_OK;
+    return timing_end(e, st);
 }
 
 extern "C" int mt_sample_actions(mt_env *e, float *actions_dev, void *stream) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
     if (int rc = check_ptr(actions_dev, "actions_dev", true)) return rc;
     DeviceGuard guard(e->cfg.device);
-    StepParams P = e->base;
-    P.step_lo = (uint32_t)e->step_index;
-    P.step_hi = (uint32_t)(e->step_index >> 32);
-    sample_actions_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(P, actions_dev);
+    sample_actions_kernel<<<blocks_for(e->n), 256, 0, (cudaStream_t)stream>>>(e->base, actions_dev);
     CU(cudaGetLastError());
     e->launches++;
     return MT_OK;
@@ -805,21 +861,26 @@ extern "C" int mt_rollout_random(mt_env *e, int32_t n_steps, float *obs_dev, flo
     if (n_steps < 0) return fail(MT_ERR_INVALID, "n_steps < 0");
     int rc;
     if ((rc = check_ptr(obs_dev, "obs_dev", false))) return rc;
-    if (!reward_dev || !done_dev) return fail(MT_ERR_INVALID, "reward_dev/done_dev is NULL");
     DeviceGuard guard(e->cfg.device);
+    if (!reward_dev || !done_dev) {                   // outputs nobody reads: buffers the handle owns
+        if (!e->scratch_reward) {
+            CU(cudaMalloc((void **)&e->scratch_reward, (size_t)e->n_pad * 4));
+            CU(cudaMalloc((void **)&e->scratch_done, (size_t)e->n_pad));
+        }
+        if (!reward_dev) reward_dev = e->scratch_reward;
+        if (!done_dev) done_dev = e->scratch_done;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = timing_begin(e, st))) return rc;
     for (int s = 0; s < n_steps; ++s) {
         if ((rc = launch_step(e, nullptr, obs_dev, reward_dev, done_dev, nullptr, true, 0, e->n_tiles, st))) return rc;
-        e->step_index++;
-        e->env_steps += e->n;
     }
     return timing_end(e, st);
 }
 
 extern "C" int mt_host_alloc(void **out, uint64_t bytes) {
     if (!out) return fail(MT_ERR_INVALID, "out is NULL");
-    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    CU(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped));
     return MT_OK;
 }
 extern "C" int mt_host_free(void *p) {
@@ -827,6 +888,13 @@ extern "C" int mt_host_free(void *p) {
     return MT_OK;
 }
 
+// Host-buffer step.  Default: chunks of whole tiles round-robin over internal streams, each chunk
+// H2D(actions) -> step kernel -> D2H(observations), then reward/done in two copies at the end; the
+// copies of one chunk overlap the kernels and copies of the others, and the whole call is bound by the
+// PCIe read-back of the observations (120 of the 125 B per env).  The internal streams are ordered after
+// everything submitted earlier to blocking streams (an event on the legacy default stream), not by a
+// device-wide synchronisation.  MT_HOST_ZEROCOPY=1 selects the variant that hands the pinned host
+// buffers to ONE step launch directly (actions read and results written across PCIe by the kernel).
 extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_host, float *reward_host,
                             uint8_t *done_host) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
@@ -834,15 +902,30 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
     if (!actions_host || !reward_host || !done_host) return fail(MT_ERR_INVALID, "NULL host buffer");
     DeviceGuard guard(e->cfg.device);
     const size_t J = e->cfg.n_joints, R = 3 * (size_t)e->cfg.n_obj;
+    if (!e->hs[0]) {
+        for (auto &s : e->hs) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto &v : e->hev) CU(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
+        const char *zc = std::getenv("MT_HOST_ZEROCOPY");
+        e->zero_copy = zc && zc[0] == '1';
+    }
+    CU(cudaEventRecord(e->hev[mt_env::kStreams], nullptr));       // everything submitted so far (blocking streams)
+    if (e->zero_copy) {
+        int rc;
+        if ((rc = check_ptr(actions_host, "actions_host", true))) return rc;
+        if ((rc = check_ptr(obs_host, "obs_host", false))) return rc;
+        CU(cudaStreamWaitEvent(e->hs[0], e->hev[mt_env::kStreams], 0));
+        if ((rc = launch_step(e, actions_host, obs_host, reward_host, done_host, nullptr, false, 0, e->n_tiles, e->hs[0])))
+            return rc;
+        CU(cudaStreamSynchronize(e->hs[0]));
+        return MT_OK;
+    }
     if (!e->h_actions) {
         CU(cudaMalloc((void **)&e->h_actions, (size_t)e->n_pad * J * 4));
         CU(cudaMalloc((void **)&e->h_obs, (size_t)e->n_pad * R * 4));
         CU(cudaMalloc((void **)&e->h_reward, (size_t)e->n_pad * 4));
         CU(cudaMalloc((void **)&e->h_done, (size_t)e->n_pad));
-        for (auto &s : e->hs) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     }
-    CU(cudaDeviceSynchronize());
-    // chunks of whole tiles, round-robin over the streams: H2D(actions) -> step -> D2H(results)
+    for (auto &s : e->hs) CU(cudaStreamWaitEvent(s, e->hev[mt_env::kStreams], 0));
     const long long chunks = e->n_tiles < 16 ? 1 : 16;
     const long long per = (e->n_tiles + chunks - 1) / chunks;
     int k = 0;
@@ -851,16 +934,20 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
         const long long e0 = t0 * kTile, e1 = (t1 * kTile < e->n) ? t1 * kTile : e->n, cnt = e1 - e0;
         cudaStream_t st = e->hs[k % mt_env::kStreams];
         CU(cudaMemcpyAsync(e->h_actions + e0 * J, actions_host + e0 * J, cnt * J * 4, cudaMemcpyHostToDevice, st));
+        // every chunk has its own launch ticket (the chunks overlap in time); the last one completes the step
         if (int rc = launch_step(e, e->h_actions, obs_host ? e->h_obs : nullptr, e->h_reward, e->h_done, nullptr, false,
-                                 t0, t1, st))
+                                 t0, t1, st, 1 + k, t1 == e->n_tiles))
             return rc;
         if (obs_host) CU(cudaMemcpyAsync(obs_host + e0 * R, e->h_obs + e0 * R, cnt * R * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(reward_host + e0, e->h_reward + e0, cnt * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(done_host + e0, e->h_done + e0, cnt, cudaMemcpyDeviceToHost, st));
     }
-    for (auto &s : e->hs) CU(cudaStreamSynchronize(s));
-    e->step_index++;
-    e->env_steps += e->n;
+    // reward / done of the whole shard: two copies once every chunk's kernel has run
+    for (int i = 1; i < mt_env::kStreams; ++i) {
+        CU(cudaEventRecord(e->hev[i], e->hs[i]));
+        CU(cudaStreamWaitEvent(e->hs[0], e->hev[i], 0));
+    }
+    CU(cudaMemcpyAsync(reward_host, e->h_reward, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->hs[0]));
+    CU(cudaMemcpyAsync(done_host, e->h_done, (size_t)e->n, cudaMemcpyDeviceToHost, e->hs[0]));
+    CU(cudaStreamSynchronize(e->hs[0]));
     return MT_OK;
 }
 
@@ -912,35 +999,46 @@ extern "C" int mt_set_objective_stream(mt_env *e, const float *points_dev, int32
     return MT_OK;
 }
 
+// one env's state packed into the handle's scratch: goals[J] | joints[J][3] | points[X][3] (dead -> 0) | alive | total
+__global__ void fetch_kernel(const __grid_constant__ StepParams P, int arm, long long index, float *out) {
+    const int J = P.n_joints, X = P.n_obj, lane = threadIdx.x;
+    const uint32_t alive = alive_mask_of(P, P.alive[index]);
+    float *goals = out, *joints = out + J, *points = out + J * 4, *tail = out + J * 4 + X * 3;
+    if (lane == 0) {
+        float g[MT_MAX_JOINTS], jb[MT_MAX_JOINTS * 3];
+        for (int k = 0; k < J; ++k) goals[k] = g[k] = P.goals[index * J + k];
+        Frames f;
+        pose_of(P, arm, g, f, jb);
+        for (int k = 0; k < J * 3; ++k) joints[k] = jb[k];
+        tail[0] = __uint_as_float(alive);
+        tail[1] = P.total_reward[index];
+    }
+    for (int i = lane; i < X * 3; i += 32) {                                // dead objectives read as zeros, manytor.py:148
+        const int pt = i / 3;
+        points[i] = ((alive >> pt) & 1u) ? P.points[index * 3 * X + point_index(P.pair_layout != 0, pt, i % 3)] : 0.f;
+    }
+}
+
+// Synchronous, on the legacy default stream (ordered after everything submitted to blocking streams):
+// one small kernel into the handle's scratch and one copy to its pinned mirror -- no allocation and no
+// device-wide synchronisation per call.
 extern "C" int mt_fetch_env(mt_env *e, int64_t index, float *goals_host, float *joints_host, float *points_host,
                             uint32_t *alive_host, float *total_reward_host) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
     if (index < 0 || index >= e->n) return fail(MT_ERR_INVALID, "env index %lld outside [0, %lld)", (long long)index, e->n);
     DeviceGuard guard(e->cfg.device);
-    const size_t J = e->cfg.n_joints, X = e->cfg.n_obj;
-    CU(cudaDeviceSynchronize());
-    uint32_t alive = 0;
-    CU(cudaMemcpy(&alive, e->alive + index, 4, cudaMemcpyDeviceToHost));
-    alive = alive_mask_of(e->base, alive);
-    if (alive_host) *alive_host = alive;
-    if (goals_host) CU(cudaMemcpy(goals_host, e->goals + index * J, J * 4, cudaMemcpyDeviceToHost));
-    if (total_reward_host) CU(cudaMemcpy(total_reward_host, e->total_reward + index, 4, cudaMemcpyDeviceToHost));
-    if (points_host) {
-        float raw[MT_MAX_OBJ * 3];
-        CU(cudaMemcpy(raw, e->points + index * X * 3, X * 12, cudaMemcpyDeviceToHost));
-        for (size_t p = 0; p < X; ++p)
-            for (int c = 0; c < 3; ++c)                                 // dead objectives read as zeros, manytor.py:148
-                points_host[p * 3 + c] = ((alive >> p) & 1u) ? raw[point_index(e->base.pair_layout != 0, (int)p, c)] : 0.f;
-    }
-    if (joints_host) {
-        float *tmp = nullptr;
-        CU(cudaMalloc((void **)&tmp, J * 12));
-        joints_kernel<<<1, 32>>>(e->base, e->arm, e->goals + index * J, 1, tmp);
-        cudaError_t ce = cudaMemcpy(joints_host, tmp, J * 12, cudaMemcpyDeviceToHost);
-        cudaFree(tmp);
-        CU(ce);
-        e->launches++;
-    }
+    const size_t J = e->cfg.n_joints, X = e->cfg.n_obj, words = J * 4 + X * 3 + 2;
+    fetch_kernel<<<1, 32, 0, nullptr>>>(e->base, e->arm, index, e->fetch_dev);
+    CU(cudaGetLastError());
+    e->launches++;
+    CU(cudaMemcpyAsync(e->fetch_host, e->fetch_dev, words * 4, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    const float *h = e->fetch_host;
+    if (goals_host) std::memcpy(goals_host, h, J * 4);
+    if (joints_host) std::memcpy(joints_host, h + J, J * 12);
+    if (points_host) std::memcpy(points_host, h + J * 4, X * 12);
+    if (alive_host) std::memcpy(alive_host, h + J * 4 + X * 3, 4);
+    if (total_reward_host) *total_reward_host = h[J * 4 + X * 3 + 1];
     return MT_OK;
 }
 
@@ -949,7 +1047,7 @@ extern "C" int mt_stats_device(mt_env *e, int64_t *stats_dev, void *stream) {
     DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(stats_dev, 0, MT_STATS_WORDS * 8, st));
-    stats_kernel<<<148, 256, 0, st>>>(e->base, e->env_steps, (long long *)stats_dev);
+    stats_kernel<<<e->num_sms, 256, 0, st>>>(e->base, (long long *)stats_dev);
     CU(cudaGetLastError());
     e->launches++;
     return MT_OK;
@@ -958,23 +1056,126 @@ extern "C" int mt_stats_device(mt_env *e, int64_t *stats_dev, void *stream) {
 extern "C" int mt_stats_host(mt_env *e, mt_stats *out) {
     if (!e || !out) return fail(MT_ERR_INVALID, "NULL argument");
     DeviceGuard guard(e->cfg.device);
-    int64_t *tmp = nullptr;
-    CU(cudaMalloc((void **)&tmp, MT_STATS_WORDS * 8));
-    CU(cudaDeviceSynchronize());
-    int rc = mt_stats_device(e, tmp, nullptr);
-    cudaError_t ce = cudaSuccess;
-    if (rc == MT_OK) ce = cudaMemcpy(out, tmp, MT_STATS_WORDS * 8, cudaMemcpyDeviceToHost);
-    cudaFree(tmp);
-    if (rc) return rc;
-    CU(ce);
+    if (int rc = mt_stats_device(e, e->stats_dev, nullptr)) return rc;   // legacy default stream: after all blocking streams
+    CU(cudaMemcpyAsync(e->stats_pin, e->stats_dev, MT_STATS_WORDS * 8, cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    std::memcpy(out, e->stats_pin, MT_STATS_WORDS * 8);
+    return MT_OK;
+}
+
+// ----------------------------------------------------------------------------
+// The one collective of a multi-GPU rollout: the MT_STATS_WORDS statistics of every
+// shard summed with ncclAllReduce over NVLink.  NCCL is dlopen'ed (like NVRTC): a host that already loaded
+// one (torch) shares it, and the library has no link-time dependency on it.
+// ----------------------------------------------------------------------------
+namespace {
+struct Nccl {
+    typedef struct ncclComm *Comm;
+    int (*CommInitAll)(Comm *, int, const int *) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    static constexpr int kInt64 = 4, kSum = 0;      // ncclInt64, ncclSum (nccl.h)
+    static Nccl &get() {
+        static Nccl n;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            void *h = nullptr;
+            for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+                h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+                if (h) break;
+            }
+            if (!h) return;
+#define MT_SYM(field, sym) n.field = reinterpret_cast<decltype(n.field)>(dlsym(h, sym)); if (!n.field) return;
+            MT_SYM(CommInitAll, "ncclCommInitAll")
+            MT_SYM(CommDestroy, "ncclCommDestroy")
+            MT_SYM(AllReduce, "ncclAllReduce")
+            MT_SYM(GroupStart, "ncclGroupStart")
+            MT_SYM(GroupEnd, "ncclGroupEnd")
+            MT_SYM(GetErrorString, "ncclGetErrorString")
+#undef MT_SYM
+            n.ok = true;
+        });
+        return n;
+    }
+};
+std::mutex g_comm_mu;
+std::map<std::vector<int>, std::vector<Nccl::Comm>> g_comms;     // device list -> communicators (one per device), per process
+}  // namespace
+
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != 0) return fail(MT_ERR_CUDA, "%s failed: %s", #call, Nccl::get().GetErrorString(r_));   \
+    } while (0)
+
+// Caller-provided communicator (one process per GPU: the host created `nccl_comm` with ncclCommInitRank):
+// writes this shard's statistics to stats_dev and all-reduces them in place on `stream`.  Asynchronous.
+extern "C" int mt_stats_allreduce_comm(mt_env *e, void *nccl_comm, int64_t *stats_dev, void *stream) {
+    if (!e || !nccl_comm || !stats_dev) return fail(MT_ERR_INVALID, "NULL argument");
+    Nccl &nc = Nccl::get();
+    if (!nc.ok) return fail(MT_ERR_CUDA, "libnccl.so.2 not found (dlopen)");
+    DeviceGuard guard(e->cfg.device);
+    if (int rc = mt_stats_device(e, stats_dev, stream)) return rc;
+    NC(nc.AllReduce(stats_dev, stats_dev, MT_STATS_WORDS, Nccl::kInt64, Nccl::kSum, (Nccl::Comm)nccl_comm, (cudaStream_t)stream));
+    return MT_OK;
+}
+
+// Single process driving n handles on n DISTINCT devices: communicators come from ncclCommInitAll (made on
+// first use, cached per device list).  Synchronous; every handle's sum lands in *out_host.
+extern "C" int mt_stats_allreduce(mt_env *const *envs, int32_t n, mt_stats *out_host) {
+    if (!envs || n < 1 || !out_host) return fail(MT_ERR_INVALID, "envs/out is NULL or n < 1");
+    for (int i = 0; i < n; ++i)
+        if (!envs[i]) return fail(MT_ERR_INVALID, "envs[%d] is NULL", i);
+    if (n == 1) return mt_stats_host(envs[0], out_host);
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; ++i) {
+        devs[i] = envs[i]->cfg.device;
+        for (int k = 0; k < i; ++k)
+            if (devs[k] == devs[i]) return fail(MT_ERR_INVALID, "envs[%d] and envs[%d] share device %d: one handle per device", k, i, devs[i]);
+    }
+    Nccl &nc = Nccl::get();
+    if (!nc.ok) return fail(MT_ERR_CUDA, "libnccl.so.2 not found (dlopen)");
+    std::vector<Nccl::Comm> *comms = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_comm_mu);
+        auto hit = g_comms.find(devs);
+        if (hit == g_comms.end()) {
+            std::vector<Nccl::Comm> made(n, nullptr);
+            NC(nc.CommInitAll(made.data(), n, devs.data()));
+            hit = g_comms.emplace(devs, std::move(made)).first;
+        }
+        comms = &hit->second;
+    }
+    for (int i = 0; i < n; ++i) {
+        DeviceGuard guard(devs[i]);
+        if (int rc = mt_stats_device(envs[i], envs[i]->stats_dev, nullptr)) return rc;
+    }
+    NC(nc.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        int r = nc.AllReduce(envs[i]->stats_dev, envs[i]->stats_dev, MT_STATS_WORDS, Nccl::kInt64, Nccl::kSum, (*comms)[i], nullptr);
+        if (r != 0) {
+            nc.GroupEnd();
+            return fail(MT_ERR_CUDA, "ncclAllReduce failed: %s", nc.GetErrorString(r));
+        }
+    }
+    NC(nc.GroupEnd());
+    for (int i = 0; i < n; ++i) {
+        DeviceGuard guard(devs[i]);
+        CU(cudaStreamSynchronize(nullptr));
+    }
+    DeviceGuard guard(devs[0]);
+    CU(cudaMemcpy(out_host, envs[0]->stats_dev, MT_STATS_WORDS * 8, cudaMemcpyDeviceToHost));
     return MT_OK;
 }
 
 extern "C" int mt_stats_clear(mt_env *e, void *stream) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
     DeviceGuard guard(e->cfg.device);
-    CU(cudaMemsetAsync(e->stats, 0, (MT_STATS_WORDS + kGroundSlots) * 8, (cudaStream_t)stream));
-    e->env_steps = 0;
+    CU(cudaMemsetAsync(e->stats, 0, MT_STATS_WORDS * 8, (cudaStream_t)stream));
     return MT_OK;
 }
 

@@ -130,6 +130,13 @@ __device__ __forceinline__ void bulk_store_hint(void *dst_gmem, const void *src_
                  : "memory");
 }
 
+// a load that always goes to memory (the device-side step index is written by another block)
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *a) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+    return v;
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------
 // Consecutive step launches are data dependent (step t+1 reads the state step t wrote), but the
 // next launch's block scheduling, shared-memory carve-up and barrier setup are not.  With the

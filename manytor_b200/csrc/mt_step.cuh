@@ -31,11 +31,14 @@ constexpr int kTile = 32;
 // for the reference arm at x = 10: 72 registers, 7.7 KB of tile buffers per warp), because the warps of a
 // block share the block's tile queue (see step_kernel).  Upper bounds for __launch_bounds__:
 constexpr int kMaxWarpsRefArm = 28, kMaxWarpsGeneric = 16;
-// Ground-contact steps are counted per warp and added, once per launch, to one of kGroundSlots
-// counters behind the statistics words (slot = global warp index mod kGroundSlots): every warp of
-// a grid finishing with an atomic on ONE address was measured at +3.6 us per launch (4144
-// same-address atomics serialising in the launch's tail); spread over 2048 addresses they are free.
-constexpr int kGroundSlots = 2048;
+// Statistics and counters live on the DEVICE, so that a replayed CUDA graph counts its steps and draws
+// fresh actions (the host never sees a replay).  Every warp adds its share to accumulators in shared
+// memory; the last warp of a block flushes them with one global atomic per word (148 per launch and
+// address: every WARP finishing with a global atomic on one address was measured at +3.6 us per launch),
+// and the last block of a launch -- found with a ticket -- bumps the step index and the env-step count.
+// Control words (StepParams::ctrl, 64-bit each): [0] step index, [1 + slot] launch tickets.
+constexpr int kCtrlStep = 0, kCtrlTicket = 1, kTicketSlots = 31, kCtrlWords = kCtrlTicket + kTicketSlots;
+constexpr int kBlockStats = 6;   // episodes, terminated, reward_sum, length_sum, catches, ground_steps = mt_stats words 1..6
 
 enum StepFlags : int32_t {
     kTerminateOnGround = 1,
@@ -63,12 +66,15 @@ struct StepParams {
     uint8_t *done;           // [N]
     float *joints;           // [N][J][3] or nullptr
     const float *obj_stream; // [sets][N][X][3] or nullptr
-    unsigned long long *stats;
+    unsigned long long *stats; // [MT_STATS_WORDS]
+    unsigned long long *ctrl;  // [kCtrlWords]: step index, launch tickets (see above)
     long long n;
     long long tile_begin, tile_end;
     long long env_id_base;
     uint32_t seed_lo, seed_hi;
-    uint32_t step_lo, step_hi;
+    int32_t ticket_slot;       // which ticket this launch uses (launches that may overlap in time use different ones)
+    int32_t advance;           // 1: this launch completes a step -> its last block increments the step index
+    long long launch_envs;     // envs this launch advances (added to the env-step count by its last block)
     int32_t n_obj, n_joints, substeps, horizon, flags, obj_sets;
     int32_t action_low;
     uint32_t action_span;
@@ -544,15 +550,16 @@ __device__ __forceinline__ void sample_point(const StepParams &P, long long gid,
     z = r * ct;
 }
 
-__device__ __forceinline__ void draw_actions(const StepParams &P, long long gid, int J, float *a) {
+__device__ __forceinline__ void draw_actions(const StepParams &P, unsigned long long step, long long gid, int J, float *a) {
     const uint32_t lo = (uint32_t)gid, hi = (uint32_t)((unsigned long long)gid >> 32);
-    Philox u = philox4x32_10(lo, hi, P.step_lo, STREAM_ACTIONS ^ P.step_hi, P.seed_lo, P.seed_hi);
+    const uint32_t step_lo = (uint32_t)step, step_hi = (uint32_t)(step >> 32);
+    Philox u = philox4x32_10(lo, hi, step_lo, STREAM_ACTIONS ^ step_hi, P.seed_lo, P.seed_hi);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (i < J) a[i] = (float)uniform_int(w[i], P.action_low, P.action_span);
     if (J > 4) {
-        Philox u2 = philox4x32_10(lo, hi, P.step_lo, (STREAM_ACTIONS + 1u) ^ P.step_hi, P.seed_lo, P.seed_hi);
+        Philox u2 = philox4x32_10(lo, hi, step_lo, (STREAM_ACTIONS + 1u) ^ step_hi, P.seed_lo, P.seed_hi);
         const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
 #pragma unroll
         for (int i = 4; i < MT_MAX_JOINTS; ++i)
@@ -634,6 +641,8 @@ __global__ void __launch_bounds__(((ARM == 0) ? kMaxWarpsRefArm : kMaxWarpsGener
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int queue_next;
+    __shared__ unsigned int warps_done;
+    __shared__ unsigned long long blk_stat[kBlockStats];
     constexpr int J = ArmJoints<ARM>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int x = X ? X : P.n_obj;
@@ -672,7 +681,12 @@ step_kernel(const __grid_constant__ StepParams P) {
         bulk_load_hint(tile_buf(b), P.points + (size_t)tile * (size_t)(kTile * rowlen), tile_bytes, bar + b, pol_stream);
     };
 
-    if (threadIdx.x == 0) queue_next = wpb;     // the first wpb tiles of the block go to its warps directly
+    if (threadIdx.x == 0) {
+        queue_next = wpb;                   // the first wpb tiles of the block go to its warps directly
+        warps_done = 0u;
+#pragma unroll
+        for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
+    }
     __syncthreads();
     int cur = tile_of(warp);
 #ifdef MT_TRACE
@@ -680,167 +694,183 @@ step_kernel(const __grid_constant__ StepParams P) {
     unsigned trace_tiles = 0;
 #endif
     griddep_launch_dependents();            // the next step's grid may start taking free SM slots
-    if (cur < 0) return;
-    if (lane == 0) {
+    if (cur >= 0 && lane == 0) {
         mbar_init(bar, 1);
         if (NB == 2) mbar_init(bar + 1, 1);
         mbar_init_fence();
     }
     griddep_wait();                         // ... but nothing touches the state before the previous step is complete
-    if (lane == 0) fetch_points(cur, 0);
-    __syncwarp();
-    TileScalars<J> sc;
-    load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
-    int nxt = grab_tile();
-    int b = 0;
-    uint32_t phase0 = 0, phase1 = 0;
-    const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
     uint32_t ground_steps = 0;              // warp-uniform: ground-contact env-steps of this warp's tiles
-
-    while (true) {
-        const int env0 = cur * kTile, env32 = env0 + lane;
-        const size_t env = (size_t)env32;
-        const bool full = env0 + kTile <= n_envs;  // warp-uniform
-        const bool valid = env32 < n_envs;
-
-        // 1. next tile's scalars on their way to registers
-        TileScalars<J> sn;
-        if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
-
-        // 2. kinematics of the current tile (needs no objectives)
-        if (RAND) draw_actions(P, P.env_id_base + env32, J, sc.a);
-        Frames f;
-        float jbuf[J * 3];
-        float *jout = P.joints ? jbuf : nullptr;
-        if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, jout);
-        else generic_arm<ARM>(P, sc.g, sc.a, f, jout);
-        const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
-
-        // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous
-        //    contents, tile i-1's observations, have long been read out by their bulk store)
-        if (NB == 2 && nxt >= 0 && lane == 0) {
-            if (WOBS) bulk_wait_read0();
-            fetch_points(nxt, b ^ 1);
-        }
-
-        // 4. objectives of the current tile: obs2 in place + catch mask
-        mbar_wait(bar + b, b ? phase1 : phase0);
-        if (b) phase1 ^= 1u; else phase0 ^= 1u;
-        float *row = tile_buf(b) + lane * rowlen;
-        const uint32_t alive0 = sc.alive & amask;
-        const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
-        uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
-
-        // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
-        float rew = (alive1 != alive0) ? 1.0f : 0.0f;
-        rew = neg ? -1.0f : rew;
-        float total = sc.total + rew;
-        uint32_t eplen = min((P.ep_shift ? sc.alive >> P.ep_shift : sc.cnt) + 1u, P.ep_max);
-        ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
-        bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
-        bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
-        const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
-
-        // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32).
-        //    Rare (one env-step in ~550 for random actions), so the warp handles its ending envs
-        //    one at a time and COOPERATIVELY: lane p draws objective p (x <= 32 lanes busy) instead
-        //    of the one ending lane drawing all x while 31 lanes idle.
-        float gn[J];
-#pragma unroll
-        for (int i = 0; i < J; ++i) gn[i] = sc.a[i];                      // goals <- action (manytor.py:184)
-        const bool ending = ((P.flags & kAutoReset) != 0) & (done != 0) & valid;
-        uint32_t pending = __ballot_sync(0xffffffffu, ending);
-        if (ending) {
-            atomicAdd(P.stats + 1, 1ull);
-            atomicAdd(P.stats + 2, term ? 1ull : 0ull);
-            atomicAdd(P.stats + 3, (unsigned long long)(long long)total);
-            atomicAdd(P.stats + 4, (unsigned long long)eplen);
-            atomicAdd(P.stats + 5, (unsigned long long)(x - __popc(alive1)));
-#pragma unroll
-            for (int i = 0; i < J; ++i) gn[i] = 0.f;
-            alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
-            total = 0.f;
-            eplen = 0u;
-        }
-        while (pending) {
-            const int src = __ffs(pending) - 1;
-            pending &= pending - 1u;
-            const size_t renv = (size_t)(env0 + src);
-            const uint32_t ep = P.episode[renv];                           // resets so far (broadcast load)
-            __syncwarp();
-            if (lane == src) P.episode[renv] = ep + 1u;
-            if (lane < x) {
-                float px, py, pz;
-                if (P.obj_stream) {
-                    const float *srcp = P.obj_stream + (((size_t)(ep % (uint32_t)P.obj_sets) * (size_t)P.n + renv) * x + lane) * 3;
-                    px = srcp[0]; py = srcp[1]; pz = srcp[2];
-                } else {
-                    sample_point(P, P.env_id_base + (long long)renv, ep, lane, px, py, pz);
-                }
-                float *grow = P.points + renv * rowlen;
-                grow[point_index((x & 1) == 0, lane, 0)] = px;
-                grow[point_index((x & 1) == 0, lane, 1)] = py;
-                grow[point_index((x & 1) == 0, lane, 2)] = pz;
-                if (WOBS && (P.flags & kObsAfterReset)) {
-                    Frames f0;
-                    f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
-                    f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
-                    one_objective<true>(px, py, pz, f0, P.catch_tol, true);
-                    float *orow = tile_buf(b) + src * rowlen + lane * 3;
-                    orow[0] = px; orow[1] = py; orow[2] = pz;
-                }
-            }
-        }
+    if (cur >= 0) {                         // (a warp without a tile still takes part in the block's epilogue)
+        // the step index keys the in-kernel action stream; it lives in device memory and was advanced by the
+        // previous launch's last block (visible here: griddepcontrol.wait orders after that grid's completion)
+        unsigned long long step_index = 0ull;
+        if (RAND) step_index = ld_volatile_u64(P.ctrl + kCtrlStep);
+        if (lane == 0) fetch_points(cur, 0);
         __syncwarp();
+        TileScalars<J> sc;
+        load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
+        int nxt = grab_tile();
+        int b = 0;
+        uint32_t phase0 = 0, phase1 = 0;
+        const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
 
-        // 7. write back: state (coalesced), then the observation tile by one bulk store
-        if (J == 4) {
-            st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
-        } else {
-#pragma unroll
-            for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, gn[i], pol_keep);
-        }
-        st_hint(P.alive + env, P.ep_shift ? (alive1 | (eplen << P.ep_shift)) : alive1, pol_keep);
-        st_hint(P.total_reward + env, total, pol_keep);
-        if (!P.ep_shift) st_hint(P.counters + env, eplen, pol_keep);
-        if (valid) {
-            st_hint(P.reward + env, rew, pol_stream);
-            st_hint(P.done + env, done, pol_stream);
-            if (P.joints) {
-#pragma unroll
-                for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
+        while (true) {
+            const int env0 = cur * kTile, env32 = env0 + lane;
+            const size_t env = (size_t)env32;
+            const bool full = env0 + kTile <= n_envs;  // warp-uniform
+            const bool valid = env32 < n_envs;
+
+            // 1. next tile's scalars on their way to registers
+            TileScalars<J> sn;
+            if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
+
+            // 2. kinematics of the current tile (needs no objectives)
+            if (RAND) draw_actions(P, step_index, P.env_id_base + env32, J, sc.a);
+            Frames f;
+            float jbuf[J * 3];
+            float *jout = P.joints ? jbuf : nullptr;
+            if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, jout);
+            else generic_arm<ARM>(P, sc.g, sc.a, f, jout);
+            const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
+
+            // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous
+            //    contents, tile i-1's observations, have long been read out by their bulk store)
+            if (NB == 2 && nxt >= 0 && lane == 0) {
+                if (WOBS) bulk_wait_read0();
+                fetch_points(nxt, b ^ 1);
             }
-        }
-        if (WOBS) {
-            if (full) {
-                fence_async_smem();
-                __syncwarp();
+
+            // 4. objectives of the current tile: obs2 in place + catch mask
+            mbar_wait(bar + b, b ? phase1 : phase0);
+            if (b) phase1 ^= 1u; else phase0 ^= 1u;
+            float *row = tile_buf(b) + lane * rowlen;
+            const uint32_t alive0 = sc.alive & amask;
+            const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
+            uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
+
+            // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
+            float rew = (alive1 != alive0) ? 1.0f : 0.0f;
+            rew = neg ? -1.0f : rew;
+            float total = sc.total + rew;
+            uint32_t eplen = min((P.ep_shift ? sc.alive >> P.ep_shift : sc.cnt) + 1u, P.ep_max);
+            ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
+            bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
+            bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
+            const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
+
+            // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32).
+            //    Rare (one env-step in ~550 for random actions), so the warp handles its ending envs
+            //    one at a time and COOPERATIVELY: lane p draws objective p (x <= 32 lanes busy) instead
+            //    of the one ending lane drawing all x while 31 lanes idle.
+            float gn[J];
+#pragma unroll
+            for (int i = 0; i < J; ++i) gn[i] = sc.a[i];                      // goals <- action (manytor.py:184)
+            const bool ending = ((P.flags & kAutoReset) != 0) & (done != 0) & valid;
+            uint32_t pending = __ballot_sync(0xffffffffu, ending);
+            if (pending) {                                                     // warp-uniform, rare
+                // fold the ending episodes into the block's statistics: one warp reduction per word and one
+                // shared-memory atomic from lane 0 (five same-address GLOBAL atomics per ending env before)
+                const uint32_t n_term = __popc(__ballot_sync(0xffffffffu, ending & term));
+                const int r_sum = __reduce_add_sync(0xffffffffu, ending ? (int)total : 0);
+                const uint32_t l_sum = __reduce_add_sync(0xffffffffu, ending ? eplen : 0u);
+                const uint32_t c_sum = __reduce_add_sync(0xffffffffu, ending ? (uint32_t)(x - __popc(alive1)) : 0u);
                 if (lane == 0) {
-                    bulk_store_hint(P.obs + (size_t)env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
-                    bulk_commit();
+                    atomicAdd(&blk_stat[0], (unsigned long long)__popc(pending));
+                    atomicAdd(&blk_stat[1], (unsigned long long)n_term);
+                    atomicAdd(&blk_stat[2], (unsigned long long)(long long)r_sum);
+                    atomicAdd(&blk_stat[3], (unsigned long long)l_sum);
+                    atomicAdd(&blk_stat[4], (unsigned long long)c_sum);
                 }
-            } else if (valid) {
-                float *dst = P.obs + env * rowlen;
-                for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
             }
-        }
+            if (ending) {
+#pragma unroll
+                for (int i = 0; i < J; ++i) gn[i] = 0.f;
+                alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
+                total = 0.f;
+                eplen = 0u;
+            }
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1u;
+                const size_t renv = (size_t)(env0 + src);
+                const uint32_t ep = P.episode[renv];                           // resets so far (broadcast load)
+                __syncwarp();
+                if (lane == src) P.episode[renv] = ep + 1u;
+                if (lane < x) {
+                    float px, py, pz;
+                    if (P.obj_stream) {
+                        const float *srcp = P.obj_stream + (((size_t)(ep % (uint32_t)P.obj_sets) * (size_t)P.n + renv) * x + lane) * 3;
+                        px = srcp[0]; py = srcp[1]; pz = srcp[2];
+                    } else {
+                        sample_point(P, P.env_id_base + (long long)renv, ep, lane, px, py, pz);
+                    }
+                    float *grow = P.points + renv * rowlen;
+                    grow[point_index((x & 1) == 0, lane, 0)] = px;
+                    grow[point_index((x & 1) == 0, lane, 1)] = py;
+                    grow[point_index((x & 1) == 0, lane, 2)] = pz;
+                    if (WOBS && (P.flags & kObsAfterReset)) {
+                        Frames f0;
+                        f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
+                        f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
+                        one_objective<true>(px, py, pz, f0, P.catch_tol, true);
+                        float *orow = tile_buf(b) + src * rowlen + lane * 3;
+                        orow[0] = px; orow[1] = py; orow[2] = pz;
+                    }
+                }
+            }
+            __syncwarp();
+
+            // 7. write back: state (coalesced), then the observation tile by one bulk store
+            if (J == 4) {
+                st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
+            } else {
+#pragma unroll
+                for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, gn[i], pol_keep);
+            }
+            st_hint(P.alive + env, P.ep_shift ? (alive1 | (eplen << P.ep_shift)) : alive1, pol_keep);
+            st_hint(P.total_reward + env, total, pol_keep);
+            if (!P.ep_shift) st_hint(P.counters + env, eplen, pol_keep);
+            if (valid) {
+                st_hint(P.reward + env, rew, pol_stream);
+                st_hint(P.done + env, done, pol_stream);
+                if (P.joints) {
+#pragma unroll
+                    for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
+                }
+            }
+            if (WOBS) {
+                if (full) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_store_hint(P.obs + (size_t)env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
+                        bulk_commit();
+                    }
+                } else if (valid) {
+                    float *dst = P.obs + env * rowlen;
+                    for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
+                }
+            }
 
 #ifdef MT_TRACE
-        ++trace_tiles;
+            ++trace_tiles;
 #endif
-        if (nxt < 0) break;
-        if (NB == 1) {   // single buffer: refill it as soon as the observations have been read out
-            __syncwarp();
-            if (lane == 0) {
-                if (WOBS) bulk_wait_read0();
-                fetch_points(nxt, 0);
+            if (nxt < 0) break;
+            if (NB == 1) {   // single buffer: refill it as soon as the observations have been read out
+                __syncwarp();
+                if (lane == 0) {
+                    if (WOBS) bulk_wait_read0();
+                    fetch_points(nxt, 0);
+                }
             }
+            cur = nxt;
+            nxt = grab_tile();
+            sc = sn;
+            if (NB == 2) b ^= 1;
+            __syncwarp();
         }
-        cur = nxt;
-        nxt = grab_tile();
-        sc = sn;
-        if (NB == 2) b ^= 1;
-        __syncwarp();
+        if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
     }
 #ifdef MT_TRACE
     if (lane == 0) {
@@ -852,10 +882,27 @@ step_kernel(const __grid_constant__ StepParams P) {
         }
     }
 #endif
-    if (lane == 0 && ground_steps)
-        atomicAdd(P.stats + MT_STATS_WORDS + ((blockIdx.x * wpb + warp) & (kGroundSlots - 1)),
-                  (unsigned long long)ground_steps);
-    if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read
+    // Epilogue.  Warp -> block: shared-memory accumulators; the block's last warp -> device: one atomic per
+    // non-zero word; the launch's last block (ticket) -> the env-step count and the step index.
+    if (lane == 0) {
+        if (ground_steps) atomicAdd(&blk_stat[5], (unsigned long long)ground_steps);
+        __threadfence_block();
+        if (atomicAdd(&warps_done, 1u) == (unsigned)wpb - 1u) {
+            __threadfence_block();
+#pragma unroll
+            for (int k = 0; k < kBlockStats; ++k) {
+                const unsigned long long v = reinterpret_cast<volatile unsigned long long *>(blk_stat)[k];
+                if (v) atomicAdd(P.stats + 1 + k, v);
+            }
+            __threadfence();
+            unsigned int *ticket = reinterpret_cast<unsigned int *>(P.ctrl + kCtrlTicket + P.ticket_slot);
+            if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+                atomicExch(ticket, 0u);
+                atomicAdd(P.stats, (unsigned long long)P.launch_envs);
+                if (P.advance) atomicAdd(P.ctrl + kCtrlStep, 1ull);
+            }
+        }
+    }
 }
 
 }  // namespace mt

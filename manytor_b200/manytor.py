@@ -20,7 +20,14 @@ caller can see:
     ``as_lists=False`` to get (N, 3X)/(N,)/(N,) numpy arrays over pinned host
     buffers without the per-env Python objects;
   * rendering is off the hot path: frames are produced from a copy-back of the
-    rendered env(s) only (``render_envs``), over the reference's UDP protocol.
+    rendered env(s) only (``render_envs``), over the reference's UDP protocol;
+  * ``trajectory`` (manytor.py:135,190,223: the terminal's position at every one of the
+    25 sub-poses of every step since the last reset) is materialised when it is READ, from
+    the logged (pose before, action) pairs, by one batched kinematics launch -- the step
+    itself only appends the pair.  ``Multienv`` logs it for up to 4096 envs by default
+    (``track_trajectory``);
+  * with ``horizon`` > 0, ``done`` is also True on the step that reaches the horizon
+    (truncation; the reference's driver scripts cut episodes at ``max_steps`` the same way).
 There is no CPU fallback: without the CUDA library and a B200 these classes raise.
 """
 from __future__ import annotations
@@ -152,9 +159,44 @@ class _Renderer:
         self.udp.close()
 
 
+def _trajectory_rows(envs: BatchedEnvs, pairs) -> np.ndarray:
+    """Terminal positions over the 25 interpolated poses of each logged (pose before, action) pair
+    (manytor.py:182-190), (25 * len(pairs), 3) float64, by one batched ``mt_joints`` launch."""
+    if not pairs:
+        return np.zeros((0, 3))
+    before = np.stack([p[0] for p in pairs]).astype(np.float64)
+    action = np.stack([p[1] for p in pairs]).astype(np.float64)
+    k = np.arange(_SUBSTEPS, dtype=np.float64)[None, :, None] / (_SUBSTEPS - 1)
+    route = before[:, None, :] + k * (action - before)[:, None, :]
+    route[:, -1, :] = action                                                   # linspace pins the endpoint
+    joints = envs.joints_of(route.reshape(-1, envs.j).astype(np.float32)).cpu().numpy().astype(np.float64)
+    return joints[:, -1, :]
+
+
+class _TrajectoryLog:
+    """``trajectory`` of one env: the nominal start row of manytor.py:223 plus 25 rows per step."""
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.pairs, self.rows, self.done_pairs = [], np.array([[0.0, 0.0, 51.3]]), 0
+
+    def append(self, before, action):
+        self.pairs.append((np.array(before, dtype=np.float64), np.array(action, dtype=np.float64)))
+
+    def materialise(self, envs: BatchedEnvs) -> np.ndarray:
+        if self.done_pairs < len(self.pairs):
+            self.rows = np.vstack((self.rows, _trajectory_rows(envs, self.pairs[self.done_pairs:])))
+            self.done_pairs = len(self.pairs)
+        return self.rows if len(self.pairs) else self.rows[0]                  # manytor.py:135: a (3,) vector before the first step
+
+
 class _EnvView:
-    """``multienv.environment[i]``: attribute access to one env's state
-    (manytor.py:131-139; test_multi.py:32 reads ``total_reward``)."""
+    """``multienv.environment[i]``: one env of the batch with the reference's per-env surface
+    (manytor.py:125-260; test_multi.py:32 reads ``total_reward``).  Attribute reads copy that env's
+    state back (``mt_fetch_env``); ``step`` advances ONLY this env -- its state goes through a
+    one-env handle and back, so it is for occasional use, the batch is what ``Multienv.step`` is for."""
 
     def __init__(self, owner: "Multienv", index: int):
         self._owner, self.id = owner, index
@@ -187,6 +229,43 @@ class _EnvView:
     def rendering(self):
         return self._owner.rendering and self.id in self._owner.render_envs
 
+    @property
+    def trajectory(self):
+        return self._owner._trajectory_of(self.id)
+
+    def _one_hot(self):
+        m = np.zeros(self._owner.env_number, dtype=bool)
+        m[self.id] = True
+        return m
+
+    def get_observations(self):
+        """manytor.py:141-153."""
+        return self._owner._envs.observe().cpu().numpy().astype(np.float64)[self.id]
+
+    def is_done(self):
+        """manytor.py:155-173 on the current state."""
+        return not bool(self.alives.any())
+
+    def action_sample(self):
+        """manytor.py:215-217."""
+        return [int(v) for v in self._owner._envs.sample_actions().cpu().numpy()[self.id]]
+
+    def reset(self, returnable=False):
+        """manytor.py:219-253 for this env only."""
+        self._owner._envs.reset(mask=self._one_hot())
+        self._owner._trajectory_reset(self.id)
+        return self.get_observations() if returnable else None
+
+    def step(self, action):
+        """manytor.py:255-260 for this env only -> (obs2, reward, done)."""
+        return self._owner._step_one(self.id, action)
+
+    def render(self, stop_render=False, multienv=True):
+        """manytor.py:262-283: add this env to / remove it from the envs streamed to the viewer."""
+        envs = set(self._owner.render_envs)
+        (envs.discard if stop_render else envs.add)(self.id)
+        self._owner.render_envs = tuple(sorted(envs))
+
 
 class _EnvList(Sequence):
     def __init__(self, owner):
@@ -210,17 +289,28 @@ class Multienv:
 
     def __init__(self, env_shape=(1, 2), obj_number=5, as_lists: bool = True, device=None, seed: int = 0,
                  arm: ArmSpec = REFERENCE_ARM, horizon: int = 0, auto_reset: bool = False,
-                 terminate_on_ground: bool = False, render_envs: Sequence[int] = (0,), **kw):
+                 terminate_on_ground: bool = False, render_envs: Sequence[int] = (0,),
+                 track_trajectory: Optional[bool] = None, **kw):
         self.env_shape = env_shape
         self.env_number = env_shape[0] * env_shape[1]
         self.obj_number = obj_number
         self.rendering = False
         self.as_lists = as_lists
         self.render_envs = tuple(render_envs)
-        self._envs = BatchedEnvs(self.env_number, obj_number, arm=arm, device=device, seed=seed, horizon=horizon,
-                                 auto_reset=auto_reset, terminate_on_ground=terminate_on_ground, **kw)
+        self._kw = dict(arm=arm, device=device, seed=seed, horizon=horizon, terminate_on_ground=terminate_on_ground, **kw)
+        self._envs = BatchedEnvs(self.env_number, obj_number, auto_reset=auto_reset, **self._kw)
+        self._horizon, self._auto_reset = int(horizon), bool(auto_reset)
         self.environment = _EnvList(self)
         self._renderer: Optional[_Renderer] = None
+        self._solo: Optional[BatchedEnvs] = None
+        # trajectory log: per step the (N, J) actions; the pose before a step is the previous action
+        # (zeros after a reset).  In-kernel auto-reset moves poses without the host seeing it: no log then.
+        if track_trajectory is None:
+            track_trajectory = self.env_number <= 4096
+        self._track = bool(track_trajectory) and not auto_reset
+        self._traj_actions: List[np.ndarray] = []
+        self._traj_start = np.zeros(self.env_number, dtype=np.int64)           # first logged step of each env's episode
+        self._traj_solo = {}                                                   # env -> _TrajectoryLog after per-env calls
 
     # the batched engine, for callers that want device tensors
     @property
@@ -230,12 +320,67 @@ class Multienv:
     def reset(self, returnable=False):
         """manytor.py:106-109."""
         obs = self._envs.reset(returnable=returnable)
+        self._traj_actions, self._traj_solo = [], {}
+        self._traj_start[:] = 0
         if self._renderer is not None:
             self._renderer.send([float("nan"), float("nan"), 4])               # manytor.py:246-249
         if returnable:
             o = obs.cpu().numpy().astype(np.float64)
             return list(o) if self.as_lists else o
         return None
+
+    # -- per-env surface behind ``environment[i]`` ------------------------------
+    def _trajectory_of(self, i: int) -> np.ndarray:
+        if i in self._traj_solo:
+            return self._traj_solo[i].materialise(self._envs)
+        if not self._track:
+            return np.array([0.0, 0.0, 51.3])
+        log = _TrajectoryLog()
+        before = np.zeros(self._envs.j)
+        for a in self._traj_actions[int(self._traj_start[i]):]:
+            log.append(before, a[i])
+            before = a[i]
+        return log.materialise(self._envs)
+
+    def _solo_log(self, i: int) -> "_TrajectoryLog":
+        """Switch env i to its own log (it no longer moves in lock step with the logged batch actions)."""
+        if i not in self._traj_solo:
+            log = _TrajectoryLog()
+            if self._track:
+                before = np.zeros(self._envs.j)
+                for a in self._traj_actions[int(self._traj_start[i]):]:
+                    log.append(before, a[i])
+                    before = a[i]
+            self._traj_solo[i] = log
+        return self._traj_solo[i]
+
+    def _trajectory_reset(self, i: int):
+        self._traj_solo.pop(i, None)
+        self._traj_start[i] = len(self._traj_actions)
+
+    def _step_one(self, i: int, action):
+        if self._solo is None:
+            self._solo = BatchedEnvs(1, self.obj_number, auto_reset=False, **{**self._kw, "env_id_base": 0})
+            self._solo.reset()
+        st = self._envs.get_state()
+        one = {k: v[i:i + 1] for k, v in st.items()}
+        self._solo.set_points(self._envs.get_points(zero_dead=False)[i:i + 1])
+        self._solo.set_state(goals=one["goals"], alive=one["alive"], total_reward=one["total_reward"], ep_len=one["ep_len"])
+        before = one["goals"].cpu().numpy()[0].astype(np.float64)
+        act = np.asarray(action, dtype=np.float32).reshape(1, self._envs.j)
+        obs, rew, done = self._solo.step(act)
+        new = self._solo.get_state()
+        mask = np.zeros(self.env_number, dtype=bool)
+        mask[i] = True
+        full = {k: st[k].clone() for k in st}
+        for k in full:
+            full[k][i] = new[k][0]
+        self._envs.set_state(goals=full["goals"], alive=full["alive"], total_reward=full["total_reward"],
+                             ep_len=full["ep_len"], mask=mask)
+        self._solo_log(i).append(before, act[0])
+        d = int(done.cpu().numpy()[0])
+        return (obs.cpu().numpy().astype(np.float64)[0], int(rew.cpu().numpy()[0]),
+                bool(d) if self._horizon > 0 else bool(d & 1))
 
     def action_sample(self):
         """manytor.py:111-113: per env J integers in [-180, 180)."""
@@ -252,12 +397,19 @@ class Multienv:
         if self._renderer is not None:
             before = {i: self._envs.fetch_env(i) for i in self.render_envs if i < self.env_number}
         obs, rew, done = self._envs.step_host(act)
+        if self._track:
+            logged = np.array(act, dtype=np.float32).reshape(self.env_number, self._envs.j)   # a copy: the caller may reuse `act`
+            self._traj_actions.append(logged)
+            for i, log in self._traj_solo.items():                             # envs stepped on their own keep their own log
+                prev = log.pairs[-1][1] if log.pairs else np.zeros(self._envs.j)
+                log.append(prev, logged[i])
         if self._renderer is not None:
             for i, st in before.items():
                 self._renderer.frames(i, st["goals"], act[i], st["points"])
         if self.as_lists:
             o = obs.astype(np.float64)
-            return list(o), [int(r) for r in rew], [bool(d & 1) for d in done]
+            # bit0 = all objectives collected (manytor.py:170-171); bit1 = horizon reached (only with horizon > 0)
+            return list(o), [int(r) for r in rew], [bool(d) if self._horizon > 0 else bool(d & 1) for d in done]
         return obs, rew, done
 
     def render(self, stop_render=False):
@@ -287,9 +439,16 @@ class Environment:
         self.id = index
         self.obj_number = obj_number
         self.rendering = False
-        self.trajectory = np.array([0.0, 0.0, 51.3])                           # manytor.py:135
+        self._traj = _TrajectoryLog()                                          # manytor.py:135
+        self._pose = np.zeros(arm.n_joints)                                    # host mirror of `goals` (pose before the next step)
+        self._horizon = int(kw.get("horizon", 0))
         self._envs = BatchedEnvs(1, obj_number, arm=arm, device=device, seed=seed, env_id_base=index, **kw)
         self._renderer: Optional[_Renderer] = None
+
+    @property
+    def trajectory(self):
+        """manytor.py:135,190,223: terminal position at every sub-pose of every step since reset()."""
+        return self._traj.materialise(self._envs)
 
     # state attributes the reference exposes (manytor.py:131-139)
     @property
@@ -331,7 +490,8 @@ class Environment:
 
     def reset(self, returnable=False):
         """manytor.py:219-253."""
-        self.trajectory = np.array([0.0, 0.0, 51.3])
+        self._traj.clear()
+        self._pose = np.zeros(self._envs.j)
         obs = self._envs.reset(returnable=returnable)
         if self._renderer is not None:
             self._renderer.send([float("nan"), float("nan"), 4])
@@ -343,12 +503,17 @@ class Environment:
         """manytor.py:255-260 -> (obs2 (3X,) float64, reward int, done bool)."""
         act = np.asarray(action, dtype=np.float32).reshape(1, self._envs.j)
         before = self._envs.fetch_env(0) if self._renderer is not None else None
-        obs, rew, done, joints = self._envs.step(act, joints=True)
+        obs, rew, done = self._envs.step(act)
         obs = obs.cpu().numpy().astype(np.float64)[0]
+        d = int(done.cpu().numpy()[0])
+        self._traj.append(self._pose, act[0])                                  # manytor.py:190, materialised on read
+        self._pose = act[0].astype(np.float64)
+        if d and self._envs.cfg.auto_reset:                                    # the kernel has already reset this env
+            self._traj.clear()
+            self._pose = np.zeros(self._envs.j)
         if before is not None:
             self._renderer.frames(self.id, before["goals"], act[0], before["points"])
-            self.trajectory = np.vstack((self.trajectory, joints.cpu().numpy()[0, -1]))
-        return obs, int(rew.cpu().numpy()[0]), bool(int(done.cpu().numpy()[0]) & 1)
+        return obs, int(rew.cpu().numpy()[0]), bool(d) if self._horizon > 0 else bool(d & 1)
 
     def render(self, stop_render=False, multienv=False):
         """manytor.py:262-283."""

@@ -133,3 +133,103 @@ def lockstep(env, ora, spec, actions_fn, steps: int, on_done=None, rep: Report |
                 env.reset(mask=r.done)
                 env.set_points(fresh, mask=r.done)
     return rep
+
+
+class ChunkedOracle:
+    """One OracleEnvs interface over several smaller ones (bounded temporaries at 2^18..2^20 envs).
+
+    Exposes what `compare_step` / the lock-step loops use: n, x, spec, goals, alive, points,
+    total_reward, ep_len, step(), reset(), _row()."""
+
+    def __init__(self, n_envs: int, obj_number: int, spec, chunk: int = 1 << 16, **kw):
+        from oracle import OracleEnvs
+        self.n, self.x, self.spec = int(n_envs), int(obj_number), spec
+        self.bounds = [(a, min(a + chunk, self.n)) for a in range(0, self.n, chunk)]
+        self.parts = [OracleEnvs(b - a, obj_number, spec=spec, **kw) for a, b in self.bounds]
+
+    def _cat(self, name):
+        return np.concatenate([getattr(p, name) for p in self.parts], axis=0)
+
+    goals = property(lambda self: self._cat("goals"))
+    alive = property(lambda self: self._cat("alive"))
+    points = property(lambda self: self._cat("points"))
+    total_reward = property(lambda self: self._cat("total_reward"))
+    ep_len = property(lambda self: self._cat("ep_len"))
+
+    def _row(self, frame):
+        return self.parts[0]._row(frame)
+
+    def reset(self, mask=None, points=None):
+        for (a, b), p in zip(self.bounds, self.parts):
+            p.reset(mask=None if mask is None else mask[a:b], points=None if points is None else points[a:b])
+
+    def set_alive(self, alive):
+        for (a, b), p in zip(self.bounds, self.parts):
+            p.alive = np.array(alive[a:b], dtype=bool)
+
+    def step(self, action):
+        from oracle import StepResult
+        rs = [p.step(action[a:b]) for (a, b), p in zip(self.bounds, self.parts)]
+        return StepResult(*[np.concatenate([getattr(r, f) for r in rs], axis=0) for f in StepResult._fields])
+
+
+def lockstep_auto_reset(env, ora, spec, stream, actions_fn, steps: int, horizon: int, rep: Report | None = None,
+                        check_points: bool = True):
+    """Device auto-reset (in-kernel, objectives from the uploaded `stream` (E, N, X, 3)) against the oracle
+    reset on the host with the same sets.  The device must already hold set 0 (env.reset() after
+    set_objective_stream) and the oracle too.  Returns (report, expected statistics, reward slack, forked):
+    a near-threshold catch/done flip changes WHICH envs reset, after which the two sides are no longer
+    comparable -- the loop stops there and says so (`forked`)."""
+    rep = rep or Report()
+    n, x = ora.n, ora.x
+    sets = stream.shape[0]
+    episode = np.ones(n, dtype=np.int64)                   # resets so far
+    stats = dict(env_steps=0, episodes=0, terminated=0, reward_sum=0, length_sum=0, catches=0)
+    slack, forked = 0, False
+    for t in range(steps):
+        act = np.float32(np.asarray(actions_fn(t))).astype(np.float64)
+        alive_before, points_before = ora.alive.copy(), ora.points.copy()
+        obs, rew, done = (o.cpu().numpy() for o in env.step(act.astype(np.float32)))
+        r = ora.step(act)
+        ep_len, total = ora.ep_len, ora.total_reward
+        trunc = (ep_len >= horizon) & ~r.done if horizon > 0 else np.zeros(n, dtype=bool)
+        ended = r.done | trunc
+        st = env.get_state()
+        dev_alive_after = alive_bits_to_matrix(st["alive"].cpu().numpy(), x)
+        dev_alive = np.where(ended[:, None], r.alive, dev_alive_after)       # ended envs were reset on the device
+        bad = compare_step(rep, spec, ora, r, points_before, alive_before, obs, rew, done, dev_alive, None)
+        stats["env_steps"] += n
+        if not rep.ok():
+            break
+        if bad.any():
+            fork = (((done & 1).astype(bool) != r.done) | (dev_alive != r.alive).any(axis=1)) & bad
+            if fork.any():
+                forked = True
+                break
+            slack += 2 * int((bad & ended).sum())
+            if (bad & ~ended).any():
+                env.set_state(total_reward=total, mask=bad & ~ended)
+        assert np.array_equal((done & 2).astype(bool), trunc), "truncation flags differ"
+        if ended.any():
+            stats["episodes"] += int(ended.sum())
+            stats["terminated"] += int(r.done.sum())
+            stats["reward_sum"] += int(total[ended].sum())
+            stats["length_sum"] += int(ep_len[ended].sum())
+            stats["catches"] += int((x - r.alive[ended].sum(axis=1)).sum())
+            fresh = stream[episode % sets, np.arange(n)]
+            ora.reset(mask=ended, points=fresh)
+            episode[ended] += 1
+            assert np.all(dev_alive_after[ended]) and np.all(st["goals"].cpu().numpy()[ended] == 0)
+            assert np.all(st["ep_len"].cpu().numpy()[ended] == 0) and np.all(st["total_reward"].cpu().numpy()[ended] == 0)
+            if check_points:
+                np.testing.assert_array_equal(env.get_points(zero_dead=False).cpu().numpy()[ended],
+                                              np.float32(fresh[ended]))
+    return rep, stats, slack, forked
+
+
+def half_ball_points(rs, shape, radius=51.3):
+    """i.i.d. uniform points in the upper half ball (the law of manytor.py:228-239), vectorised."""
+    v = rs.normal(size=tuple(shape) + (3,))
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    v[..., 2] = np.abs(v[..., 2])
+    return v * (radius * rs.uniform(0, 1, size=tuple(shape) + (1,)) ** (1 / 3))

@@ -105,15 +105,15 @@ def test_library_is_sm100a_with_tma(lib):
     assert "UBLKCP" in sass
 
 
-def _build_c_host(tmp_path):
+def _build_c_host(tmp_path, name="c_host"):
     import shutil
     import subprocess
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("gcc not available")
-    exe = str(tmp_path / "c_host")
+    exe = str(tmp_path / name)
     lib_dir = os.path.dirname(_lib.library_path())
-    cmd = [gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_host.c"),
+    cmd = [gcc, "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".c"),
            "-o", exe, "-L", lib_dir, "-lmanytor_b200", f"-Wl,-rpath,{lib_dir}"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
@@ -131,6 +131,12 @@ def test_plain_c_host_links_against_the_abi(lib, tmp_path):
         assert res.returncode == 0, res.stderr
     else:
         assert res.returncode == 1 and "no CPU fallback" in res.stderr
+
+
+def test_multi_gpu_c_host_links_against_the_abi(lib, tmp_path):
+    """examples/c_host_multi.c (config 4 from plain C: one handle per GPU + mt_stats_allreduce) builds with
+    -Wall -Werror against the header; its run is a -m gpu test."""
+    _build_c_host(tmp_path, "c_host_multi")
 
 
 def test_no_prefetch_register_is_overwritten_unread():

@@ -7,7 +7,7 @@ import pytest
 from oracle import OracleEnvs, REFERENCE_ARM, UR5_ARM, sample_points_reference_stream
 from oracle.philox import device_actions
 
-from parity import Report, alive_bits_to_matrix, compare_step, lockstep
+from parity import Report, alive_bits_to_matrix, compare_step, half_ball_points, lockstep, lockstep_auto_reset
 
 pytestmark = pytest.mark.gpu
 
@@ -182,67 +182,21 @@ def test_terminate_on_ground_option(mt):
 # on-device auto-reset with an uploaded objective stream (no host round trip)
 # --------------------------------------------------------------------------
 def test_auto_reset_with_objective_stream(mt):
-    import torch
     n, x, sets, steps, horizon = 512, 2, 6, 400, 60
     rs = np.random.RandomState(31)
-    stream = np.zeros((sets, n, x, 3))
-    for s in range(sets):
-        v = rs.normal(size=(n, x, 3))
-        v /= np.linalg.norm(v, axis=-1, keepdims=True)
-        v[..., 2] = np.abs(v[..., 2])
-        stream[s] = v * (51.3 * rs.uniform(0, 1, size=(n, x, 1)) ** (1 / 3))
-    stream = np.float32(stream).astype(np.float64)
+    stream = np.float32(half_ball_points(rs, (sets, n, x))).astype(np.float64)
     env = mt.BatchedEnvs(n, x, device=0, auto_reset=True, horizon=horizon)
     env.set_objective_stream(stream)
     env.reset()                                           # takes set 0
     ora = OracleEnvs(n, x)
     ora.reset(points=stream[0])
-    episode = np.ones(n, dtype=np.int64)                  # resets so far
     rng = np.random.RandomState(32)
-    rep = Report()
-    stats = dict(episodes=0, terminated=0, reward_sum=0, length_sum=0, catches=0)
-    slack, structural = 0, False
-    for t in range(steps):
-        act = rng.randint(-180, 180, size=(n, 4)).astype(np.float64)
-        alive_before, points_before = ora.alive.copy(), ora.points.copy()
-        obs, rew, done, jn = (o.cpu().numpy() for o in env.step(act.astype(np.float32), joints=True))
-        r = ora.step(act)
-        trunc = (ora.ep_len >= horizon) & ~r.done
-        ended = r.done | trunc
-        # device state after its in-kernel reset: rebuild what the pre-reset alive mask was from `done`
-        st = env.get_state()
-        dev_alive_after = alive_bits_to_matrix(st["alive"].cpu().numpy(), x)
-        dev_alive = np.where(ended[:, None], r.alive, dev_alive_after)   # ended envs were reset on device
-        bad = compare_step(rep, REFERENCE_ARM, ora, r, points_before, alive_before, obs, rew, done, dev_alive, jn)
-        assert rep.ok(), rep.notes[:5]
-        if bad.any():
-            # near-threshold flips (already classified by compare_step).  A ground flip only moves the
-            # reward: re-sync total_reward and keep going; a catch/done flip forks the episode structure.
-            forked = (((done & 1).astype(bool) != r.done) | (dev_alive != r.alive).any(axis=1)) & bad
-            if forked.any():
-                structural = True
-                break
-            slack += 2 * int((bad & ended).sum())
-            if (bad & ~ended).any():
-                env.set_state(total_reward=ora.total_reward, mask=bad & ~ended)
-        assert np.array_equal((done & 2).astype(bool), trunc)
-        if ended.any():
-            stats["episodes"] += int(ended.sum())
-            stats["terminated"] += int(r.done.sum())
-            stats["reward_sum"] += int(ora.total_reward[ended].sum())
-            stats["length_sum"] += int(ora.ep_len[ended].sum())
-            stats["catches"] += int((x - r.alive[ended].sum(axis=1)).sum())
-            fresh = stream[episode % sets, np.arange(n)]
-            ora.reset(mask=ended, points=fresh)
-            episode[ended] += 1
-            assert np.all(dev_alive_after[ended]) and np.all(st["goals"].cpu().numpy()[ended] == 0)
-            np.testing.assert_array_equal(env.get_points(zero_dead=False).cpu().numpy()[ended],
-                                          np.float32(fresh[ended]))
+    rep, stats, slack, forked = lockstep_auto_reset(env, ora, REFERENCE_ARM, stream,
+                                                    lambda t: rng.randint(-180, 180, size=(n, 4)), steps, horizon)
     s = env.stats()
     print("auto-reset", rep.summary(), s)
     assert rep.ok(), rep.notes[:5]
-    if not structural:
-        assert s["env_steps"] == n * steps
+    if not forked:
         for k, v in stats.items():
             assert abs(s[k] - v) <= (slack if k == "reward_sum" else 0), (k, s[k], v)
         assert s["live_reward_sum"] == int(ora.total_reward.sum())
@@ -311,12 +265,10 @@ def test_back_to_back_launches_equal_synchronised_steps(mt, n):
         st = env.get_state()
         return ([v.clone() for v in st.values()], env.get_points(False).clone(), [o.clone() for o in out], env.stats())
 
-    def same(p, q, host_counter=True):
-        sp, sq = dict(p[3]), dict(q[3])
-        if not host_counter:          # env_steps is counted by the host per call, a graph replay does not pass there
-            sp.pop("env_steps"); sq.pop("env_steps")
+    def same(p, q):
+        # the statistics include env_steps: it is counted on the device, so graph replays count too
         return (all(torch.equal(u, v) for u, v in zip(p[0], q[0])) and torch.equal(p[1], q[1]) and
-                all(torch.equal(u, v) for u, v in zip(p[2], q[2])) and sp == sq)
+                all(torch.equal(u, v) for u, v in zip(p[2], q[2])) and p[3] == q[3])
 
     ref = fresh()
     for t in range(2 * k):
@@ -338,12 +290,12 @@ def test_back_to_back_launches_equal_synchronised_steps(mt, n):
             out = env2.step(acts[t])
     cg.replay(); cg.replay()
     torch.cuda.synchronize()
-    assert same(snapshot(env2, out), want, host_counter=False)
+    assert same(snapshot(env2, out), want)
     out = env2.step(acts[0])                                                 # eager launches after a captured graph
     out = env2.step(acts[1])
     out_ref = ref.step(acts[0]); torch.cuda.synchronize()
     out_ref = ref.step(acts[1]); torch.cuda.synchronize()
-    assert same(snapshot(env2, out), snapshot(ref, out_ref), host_counter=False)
+    assert same(snapshot(env2, out), snapshot(ref, out_ref))
 
 
 def test_shard_invariance(mt):
