@@ -74,33 +74,45 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-// polynomial cores shared by the scalar and packed sin/cos: sin(pi r)/r and cos(pi r) in u = r^2
+// polynomial cores shared by the scalar and packed sin/cos: sin(pi r)/r and cos(pi r) in u = r^2, |r| <= 1/4
 __device__ __forceinline__ float2 sinpi_poly2(float2 r, float2 u) {
     return mul2(fma2(fma2(fma2(bc2(-0.58907866f), u, bc2(2.5497673f)), u, bc2(-5.1677079f)), u, bc2(3.14159274f)), r);
 }
 __device__ __forceinline__ float2 cospi_poly2(float2 u) {
     return fma2(fma2(fma2(fma2(bc2(0.23132971f), u, bc2(-1.33504462f)), u, bc2(4.05870724f)), u, bc2(-4.93480206f)), u, bc2(1.0f));
 }
-
-__device__ __forceinline__ void quadrant_fix(int q, float sp, float cp, float &s, float &c) {
-    float ss = (q & 1) ? cp : sp;
-    float cc = (q & 1) ? sp : cp;
-    s = __int_as_float(__float_as_int(ss) ^ ((q & 2) << 30));
-    c = __int_as_float(__float_as_int(cc) ^ (((q + 1) & 2) << 30));
+// ... and on |r| <= 1/2 (one more term each; tools/fit_polys.py: fp32 Horner error 1.6e-7 / 1.1e-7 abs)
+__device__ __forceinline__ float2 sinpi_poly2_half(float2 r, float2 u) {
+    float2 p = fma2(bc2(0.0776594058f), u, bc2(-0.598292172f));
+    p = fma2(p, u, bc2(2.55007768f));
+    p = fma2(p, u, bc2(-5.1677103f));
+    p = fma2(p, u, bc2(3.14159274f));
+    return mul2(p, r);
+}
+__device__ __forceinline__ float2 cospi_poly2_half(float2 u) {
+    float2 p = fma2(bc2(-0.0243967157f), u, bc2(0.234937564f));
+    p = fma2(p, u, bc2(-1.33521211f));
+    p = fma2(p, u, bc2(4.05870914f));
+    p = fma2(p, u, bc2(-4.93480206f));
+    return fma2(p, u, bc2(1.0f));
 }
 
-// sin/cos of TWO angles in degrees at once (same reduction as sincos_deg; the round-to-integer
-// is done with the 1.5*2^23 magic constant so it packs too; valid for |x| < 3e8 degrees).
+// sin/cos of TWO angles in degrees at once.  Reduction in half-turns, exact for any fp32 input below
+// 3e8 degrees: t = x/180, n = rint(t) (the 1.5*2^23 magic constant makes the rounding a packed add and
+// leaves n's parity in the low mantissa bit), r = t - n in [-1/2, 1/2]; sin(pi t) = (-1)^n sin(pi r),
+// cos likewise -- ONE sign flip shared by both results.  (Round 1 reduced to quarter turns: polynomials
+// one term shorter, but a swap + two sign fix-ups per angle, 14 instructions against 3 here.)
 __device__ __forceinline__ void sincos_deg2(float2 x, float2 &s, float2 &c) {
     const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f, magic = 12582912.0f;
     float2 t = fma2(x, bc2(inv_lo), mul2(x, bc2(inv_hi)));
-    float2 m = fma2(t, bc2(2.0f), bc2(magic));      // low mantissa bits of m = rint(2t)
+    float2 m = add2(t, bc2(magic));                 // low mantissa bits of m = rint(t)
     float2 n = add2(m, bc2(-magic));
-    float2 r = fma2(n, bc2(-0.5f), t);
+    float2 r = add2(t, neg2(n));
     float2 u = mul2(r, r);
-    float2 sp = sinpi_poly2(r, u), cp = cospi_poly2(u);
-    quadrant_fix(__float_as_int(m.x), sp.x, cp.x, s.x, c.x);
-    quadrant_fix(__float_as_int(m.y), sp.y, cp.y, s.y, c.y);
+    float2 sp = sinpi_poly2_half(r, u), cp = cospi_poly2_half(u);
+    const int fx = __float_as_int(m.x) << 31, fy = __float_as_int(m.y) << 31;
+    s = make_float2(__int_as_float(__float_as_int(sp.x) ^ fx), __int_as_float(__float_as_int(sp.y) ^ fy));
+    c = make_float2(__int_as_float(__float_as_int(cp.x) ^ fx), __int_as_float(__float_as_int(cp.y) ^ fy));
 }
 
 // two SMALL angles (|x| <= 45 degrees): quadrant 0, no fix-up

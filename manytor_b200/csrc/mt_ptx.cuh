@@ -11,37 +11,62 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
-}
-
 // make the freshly initialised barrier visible to the async (TMA) proxy
 __device__ __forceinline__ void mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "MT_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MT_DONE_%=;\n\t"
-        "bra MT_WAIT_%=;\n\t"
-        "MT_DONE_%=:\n\t"
-        "}" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until the sources of all committed bulk stores have been read (smem reusable)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- the same operations on 32-bit SHARED-SPACE addresses ----------------------------------
+// The step kernel keeps its tile buffers and barriers as shared-window offsets (smem_addr() of the dynamic
+// shared memory, once, plus integer arithmetic).  Going through generic pointers instead makes ptxas
+// rebuild the shared window base (S2UR SR_CgaCtaId, ULEA ...) in every basic block that touches them --
+// some 25 instructions per tile in round 1's SASS.
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MT_WAITS_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MT_DONES_%=;\n\t"
+        "bra MT_WAITS_%=;\n\t"
+        "MT_DONES_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+// one thread's atomic on a shared counter (written as PTX so that ptxas does not wrap it into its
+// warp-aggregation sequence: the caller already elected one lane)
+__device__ __forceinline__ int atom_add_s(uint32_t a, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
 
 // ---- L2 eviction policies -------------------------------------------------------------
 // The per-env state (goals, alive, total_reward, counters: 28 B/env) is read AND rewritten by
@@ -115,18 +140,18 @@ __device__ __forceinline__ void st_hint(uint8_t *a, uint8_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"((uint32_t)v), "l"(pol) : "memory");
 }
 // HBM -> shared, completion counted in bytes on `bar`; 16-byte aligned, size % 16 == 0; `pol` = L2 eviction policy
-__device__ __forceinline__ void bulk_load_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
-                                               uint64_t pol) {
+__device__ __forceinline__ void bulk_load_hint_s(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar,
+                                                 uint64_t pol) {
     asm volatile(
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_addr(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)), "l"(pol)
+            dst_smem),
+        "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol)
         : "memory");
 }
 // shared -> HBM as part of the thread's current bulk group
-__device__ __forceinline__ void bulk_store_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+__device__ __forceinline__ void bulk_store_hint_s(void *dst_gmem, uint32_t src_smem, uint32_t bytes, uint64_t pol) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
-                 "r"(smem_addr(src_smem)), "r"(bytes), "l"(pol)
+                 "r"(src_smem), "r"(bytes), "l"(pol)
                  : "memory");
 }
 

@@ -148,6 +148,25 @@ struct CosSeq2 {
     }
 };
 
+// ONE cosine sequence x(k) = amp cos(theta - k delta) at two sub-poses at once: lane .x holds an odd k,
+// lane .y the next even k, and back() moves both by 2 delta (Reinsch's recurrence with step 2 delta,
+// -4 sin^2(delta) shared by the lanes).  init: (ax, ay) = amp (cos, sin) theta, (sd, cd) = sin/cos delta;
+// the lanes start at k = -1 and k = 0, so that the first back() yields k = 1 and k = 2.
+struct CosPair {
+    float2 x, d;
+    float na;
+    __device__ __forceinline__ void init(float ax, float ay, float sd, float cd) {
+        const float q = (ay + ay) * sd;                       // 2 amp sin(theta) sin(delta) = x(1) - x(-1)
+        na = -4.0f * (sd * sd);
+        x = make_float2(fmaf(ax, cd, -(ay * sd)), ax);        // amp cos(theta + delta), amp cos(theta)
+        d = make_float2(q, fmaf(q, cd, 0.5f * na * ax));      // x(2) - x(0) = amp (sin th sin 2 delta - 2 sin^2 delta cos th)
+    }
+    __device__ __forceinline__ void back() {
+        x = add2(x, d);
+        d = fma2(bc2(na), x, d);
+    }
+};
+
 __device__ __forceinline__ void ref_arm(const float *g, const float *a, int substeps, float inv_div, Frames &f,
                                         float *jout /* 12 floats or nullptr */) {
     float2 s01, c01, s23, c23;
@@ -175,40 +194,69 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
     }
     float zmin = fminf(ez, tz);
     if (substeps > 1) {
-        // half steps in degrees; the small-angle sin/cos holds for |half step| <= 45, i.e. any
-        // target within +-2160 degrees of the current pose at 25 sub-poses (else: general path)
-        const float hs = 0.5f * inv_div;
-        const float2 h12 = make_float2((a[1] - g[1]) * hs, (a[2] - g[2]) * hs);
-        const float2 h33 = bc2((a[3] - g[3]) * hs);
-        float2 sh12, ch12, sh33, ch33;
-        const bool small = fmaxf(fmaxf(fabsf(h12.x), fabsf(h12.y)), fabsf(h33.x)) <= 45.0f;
-        if (__all_sync(__activemask(), small)) {
-            sincos_deg_small2(h12, sh12, ch12);
-            sincos_deg_small2(h33, sh33, ch33);
-        } else {
-            sincos_deg2(h12, sh12, ch12);
-            sincos_deg2(h33, sh33, ch33);
-        }
-        // A = th1 + th3, B = th1 - th3 and their half steps by angle addition, A in .x, B in .y:
-        // cos(th1 +- th3) = c1 c3 -+ s1 s3, sin(th1 +- th3) = s1 c3 +- c1 s3
-        const float2 pm = make_float2(1.0f, -1.0f);
-        const float2 cAB = fma2(bc2(-(s1 * s3)), pm, bc2(c1 * c3));
-        const float2 sAB = fma2(bc2(c1 * s3), pm, bc2(s1 * c3));
-        const float sh1 = sh12.x, ch1 = ch12.x, sh3 = sh33.x, ch3 = ch33.x;
-        const float2 chAB = fma2(bc2(-(sh1 * sh3)), pm, bc2(ch1 * ch3));
-        const float2 shAB = fma2(bc2(ch1 * sh3), pm, bc2(sh1 * ch3));
-        CosSeq2 q12, qAB;
-        q12.init(make_float2(L1, 1.0f), make_float2(c1, c2), make_float2(s1, s2), sh12, ch12);
-        qAB.init(bc2(0.5f * L2), cAB, sAB, shAB, chAB);
+        const float d1 = (a[1] - g[1]) * inv_div, d2 = (a[2] - g[2]) * inv_div, d3 = (a[3] - g[3]) * inv_div;   // degrees per sub-pose
+        const float dmax = fmaxf(fmaxf(fabsf(d1), fabsf(d2)), fabsf(d3));
         float m = 3.0e38f;
-#pragma unroll 8   // 4 -> 8: about -1 us per step (A/B); 24 no better, the four sequences as scalar FADD/FFMA +0.5 us
-        for (int p = 1; p < substeps; ++p) {
-            q12.back();
-            qAB.back();
-            // ee_z - 4.3 = u1 + (uA + uB) + cos(th2) (uA - uB); scalar here on purpose: a packed
-            // (sum, difference) needs a (1, -1) operand pair that ptxas re-creates every iteration
-            const float t = fmaf(q12.x.y, qAB.x.x - qAB.x.y, q12.x.x + (qAB.x.x + qAB.x.y));
-            m = fminf(m, fminf(q12.x.x, t));
+        if (((substeps - 1) & 1) == 0 && __all_sync(__activemask(), dmax <= 22.5f)) {
+            // Usual case (an even number of interior sub-poses, every joint within 540 degrees of its target at
+            // 25 sub-poses): TWO sub-poses per packed iteration.  Lane .x of every value walks the odd
+            // sub-poses k = 1, 3, ..., lane .y the even ones k = 2, 4, ..., both in steps of 2 delta, so the
+            // combination u1 + (uA + uB) + cos(th2)(uA - uB) is packed as well: 14 instructions per two
+            // sub-poses against 2 x 9.4.  Same error as the single-step recurrence (tools/emulate_subpose.py:
+            // max |dz| 3.8e-5, no ground-flag flips in 4e5 steps).
+            float2 sd12, cd12, sd33, cd33;
+            sincos_deg_small2(make_float2(d1, d2), sd12, cd12);
+            sincos_deg_small2(bc2(d3), sd33, cd33);
+            const float sd1 = sd12.x, cd1 = cd12.x, sd3 = sd33.x, cd3 = cd33.x;
+            // A = th1 + th3, B = th1 - th3: cos/sin of the angles and of their steps by angle addition
+            const float cA = fmaf(c1, c3, -(s1 * s3)), cB = fmaf(c1, c3, s1 * s3);
+            const float sA = fmaf(s1, c3, c1 * s3), sB = fmaf(s1, c3, -(c1 * s3));
+            const float cdA = fmaf(cd1, cd3, -(sd1 * sd3)), cdB = fmaf(cd1, cd3, sd1 * sd3);
+            const float sdA = fmaf(sd1, cd3, cd1 * sd3), sdB = fmaf(sd1, cd3, -(cd1 * sd3));
+            CosPair u1, q2, uA, uB;
+            u1.init(L1 * c1, L1 * s1, sd1, cd1);
+            q2.init(c2, s2, sd12.y, cd12.y);
+            uA.init(0.5f * L2 * cA, 0.5f * L2 * sA, sdA, cdA);
+            uB.init(0.5f * L2 * cB, 0.5f * L2 * sB, sdB, cdB);
+            const int iters = (substeps - 1) >> 1;
+#pragma unroll 4
+            for (int it = 0; it < iters; ++it) {
+                u1.back(); q2.back(); uA.back(); uB.back();
+                const float2 t = fma2(q2.x, add2(uA.x, neg2(uB.x)), add2(u1.x, add2(uA.x, uB.x)));
+                m = fminf(m, fminf(t.x, t.y));
+                m = fminf(m, fminf(u1.x.x, u1.x.y));
+            }
+        } else {
+            // half steps in degrees; the small-angle sin/cos holds for |half step| <= 45, i.e. any
+            // target within +-2160 degrees of the current pose at 25 sub-poses (else: general path)
+            const float2 h12 = make_float2(0.5f * d1, 0.5f * d2);
+            const float2 h33 = bc2(0.5f * d3);
+            float2 sh12, ch12, sh33, ch33;
+            if (__all_sync(__activemask(), dmax <= 90.0f)) {
+                sincos_deg_small2(h12, sh12, ch12);
+                sincos_deg_small2(h33, sh33, ch33);
+            } else {
+                sincos_deg2(h12, sh12, ch12);
+                sincos_deg2(h33, sh33, ch33);
+            }
+            // A = th1 + th3, B = th1 - th3 and their half steps by angle addition, A in .x, B in .y:
+            // cos(th1 +- th3) = c1 c3 -+ s1 s3, sin(th1 +- th3) = s1 c3 +- c1 s3
+            const float2 pm = make_float2(1.0f, -1.0f);
+            const float2 cAB = fma2(bc2(-(s1 * s3)), pm, bc2(c1 * c3));
+            const float2 sAB = fma2(bc2(c1 * s3), pm, bc2(s1 * c3));
+            const float sh1 = sh12.x, ch1 = ch12.x, sh3 = sh33.x, ch3 = ch33.x;
+            const float2 chAB = fma2(bc2(-(sh1 * sh3)), pm, bc2(ch1 * ch3));
+            const float2 shAB = fma2(bc2(ch1 * sh3), pm, bc2(sh1 * ch3));
+            CosSeq2 q12, qAB;
+            q12.init(make_float2(L1, 1.0f), make_float2(c1, c2), make_float2(s1, s2), sh12, ch12);
+            qAB.init(bc2(0.5f * L2), cAB, sAB, shAB, chAB);
+#pragma unroll 4
+            for (int p = 1; p < substeps; ++p) {
+                q12.back();
+                qAB.back();
+                const float t = fmaf(q12.x.y, qAB.x.x - qAB.x.y, q12.x.x + (qAB.x.x + qAB.x.y));
+                m = fminf(m, fminf(q12.x.x, t));
+            }
         }
         zmin = fminf(zmin, m + H);
     }
@@ -465,14 +513,15 @@ __device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 
     const bool c1 = fmaxf(fmaxf(fabsf(cx.y), fabsf(cy.y)), fabsf(cz.y)) <= tol;
     if (WOBS) {
         const float2 dx = add2(PX, bc2(-f.anchor[0])), dy = add2(PY, bc2(-f.anchor[1])), dz = add2(PZ, bc2(-f.anchor[2]));
-        const float2 h2 = fma2(dx, dx, mul2(dy, dy));
+        // 1e-36 under the square roots keeps both denominators below positive (0/0 -> 0 like math.atan2(0, 0));
+        // it is absorbed unless the objective is within 1e-15 of the anchor, where it moves the distance by 1e-18
+        const float2 h2 = fma2(dx, dx, fma2(dy, dy, bc2(1e-36f)));
         const float2 d2 = fma2(dz, dz, h2);
         const float2 h = make_float2(fast_sqrt(h2.x), fast_sqrt(h2.y));
         const float2 dist = make_float2(fast_sqrt(d2.x), fast_sqrt(d2.y));
-        // atan2(|dx|, |dy|) = 2 atan(|dx| / (|dy| + h)); atan2(h, |dz|) = 2 atan(h / (|dz| + dist)).
-        // The +1e-30 keeps 0/0 -> 0 like math.atan2(0, 0) and is absorbed by any other denominator.
-        const float2 dr = add2(add2(abs2(dy), h), bc2(1e-30f));
-        const float2 dt = add2(add2(abs2(dz), dist), bc2(1e-30f));
+        // atan2(|dx|, |dy|) = 2 atan(|dx| / (|dy| + h)); atan2(h, |dz|) = 2 atan(h / (|dz| + dist))
+        const float2 dr = add2(abs2(dy), h);
+        const float2 dt = add2(abs2(dz), dist);
         const float2 tr = mul2(abs2(dx), make_float2(fast_rcp(dr.x), fast_rcp(dr.y)));
         const float2 tt = mul2(h, make_float2(fast_rcp(dt.x), fast_rcp(dt.y)));
         const float2 R = atan_half_deg2(tr), T = atan_half_deg2(tt);
@@ -482,28 +531,26 @@ __device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 
     return (c0 ? 1u : 0u) | (c1 ? 2u : 0u);
 }
 
-// Walk one env's row of objectives in shared memory, observations written back in place.
-// Returns the bitmask of objectives inside the catch cube.
+// Walk one env's row of objectives in shared memory (`row` = its shared-space byte address),
+// observations written back in place.  Returns the bitmask of objectives inside the catch cube.
 template <int X, bool WOBS>
-__device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f, float tol, uint32_t alive) {
+__device__ __forceinline__ uint32_t walk_row(uint32_t row, int x, const Frames &f, float tol, uint32_t alive) {
     uint32_t caught = 0;
     const int xx = X ? X : x;
     if ((xx & 1) == 0) {
         // even X: pair-interleaved layout, one 64-bit access per packed operand
 #pragma unroll
         for (int pr = 0; pr < (X ? X / 2 : xx >> 1); ++pr) {
-            float *q = row + pr * 6;
-            const float2 PX = *reinterpret_cast<const float2 *>(q);
-            const float2 PY = *reinterpret_cast<const float2 *>(q + 2);
-            const float2 PZ = *reinterpret_cast<const float2 *>(q + 4);
+            const uint32_t q = row + pr * 24;
+            const float2 PX = lds_f2(q), PY = lds_f2(q + 8), PZ = lds_f2(q + 16);
             float o[6];
             const uint32_t c = pair_objective<WOBS>(PX, PY, PZ, f, tol, (alive >> (2 * pr)) & 1u,
                                                     (alive >> (2 * pr + 1)) & 1u, o);
             caught |= c << (2 * pr);
             if (WOBS) {
-                *reinterpret_cast<float2 *>(q) = make_float2(o[0], o[1]);
-                *reinterpret_cast<float2 *>(q + 2) = make_float2(o[2], o[3]);
-                *reinterpret_cast<float2 *>(q + 4) = make_float2(o[4], o[5]);
+                sts_f2(q, make_float2(o[0], o[1]));
+                sts_f2(q + 8, make_float2(o[2], o[3]));
+                sts_f2(q + 16, make_float2(o[4], o[5]));
             }
         }
     } else {
@@ -512,21 +559,24 @@ __device__ __forceinline__ uint32_t walk_row(float *row, int x, const Frames &f,
         int pt = 0;
 #pragma unroll
         for (; pt + 1 < xx; pt += 2) {
-            float *q = row + pt * 3;
-            const float2 PX = make_float2(q[0], q[3]), PY = make_float2(q[1], q[4]), PZ = make_float2(q[2], q[5]);
+            const uint32_t q = row + pt * 12;
+            float v[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) v[k] = lds_f(q + 4 * k);
             float o[6];
-            const uint32_t c = pair_objective<WOBS>(PX, PY, PZ, f, tol, (alive >> pt) & 1u, (alive >> (pt + 1)) & 1u, o);
+            const uint32_t c = pair_objective<WOBS>(make_float2(v[0], v[3]), make_float2(v[1], v[4]), make_float2(v[2], v[5]), f,
+                                                    tol, (alive >> pt) & 1u, (alive >> (pt + 1)) & 1u, o);
             caught |= c << pt;
             if (WOBS) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) q[k] = o[k];
+                for (int k = 0; k < 6; ++k) sts_f(q + 4 * k, o[k]);
             }
         }
-        float *q = row + pt * 3;
-        float px = q[0], py = q[1], pz = q[2];
+        const uint32_t q = row + pt * 12;
+        float px = lds_f(q), py = lds_f(q + 4), pz = lds_f(q + 8);
         const bool c = one_objective<WOBS>(px, py, pz, f, tol, (alive >> pt) & 1u);
         caught |= c ? (1u << pt) : 0u;
-        if (WOBS) { q[0] = px; q[1] = py; q[2] = pz; }
+        if (WOBS) { sts_f(q, px); sts_f(q + 4, py); sts_f(q + 8, pz); }
     }
     return caught;
 }
@@ -644,18 +694,30 @@ step_kernel(const __grid_constant__ StepParams P) {
     __shared__ unsigned int warps_done;
     __shared__ unsigned long long blk_stat[kBlockStats];
     constexpr int J = ArmJoints<ARM>::value;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // Everything that is the same for the whole warp is made PROVABLY warp-uniform (a warp reduction's result
+    // lives in a uniform register), so that tile indices, buffer addresses and TMA operands are computed once
+    // in the uniform datapath; with `threadIdx.x >> 5` and shuffles ptxas has to assume they diverge and wraps
+    // every bulk copy in an elect-and-broadcast loop.
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
     const int x = X ? X : P.n_obj;
     const int rowlen = 3 * x;
     const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
     // Tile buffers per warp: two for the reference arm (its kinematics are too short to cover a tile's
     // HBM latency, so tile i+1 is fetched while tile i is still being turned into observations); one
     // for the generic chain, whose long kinematics cover the fetch and where the halved footprint
-    // doubles the warps an SM can hold at X = 20.
+    // doubles the warps an SM can hold at X = 20.  Buffers and barriers are shared-space byte addresses.
     constexpr int NB = StepBuffers<ARM>::value;
-    unsigned char *tile_base = smem + (size_t)(NB * warp) * P.tile_bytes;
-    auto tile_buf = [&](int bb) { return reinterpret_cast<float *>(tile_base + (size_t)bb * P.tile_bytes); };
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)(NB * wpb) * P.tile_bytes) + NB * warp;
+    const uint32_t sbase = smem_addr(smem);
+    const uint32_t buf0 = sbase + (uint32_t)(NB * warp) * P.tile_bytes;
+    const uint32_t bar0 = sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)(NB * warp) * 8u;
+    const uint32_t queue = smem_addr(&queue_next);
+    // The warp's k-th tile uses buffer / barrier k mod NB, and a barrier's phase parity flips every time it
+    // completes, so one counter gives buffer, barrier and parity.
+    uint32_t k = 0;
+    auto buf_of = [&](uint32_t kk) { return buf0 + (NB == 2 ? (kk & 1u) * P.tile_bytes : 0u); };
+    auto bar_of = [&](uint32_t kk) { return bar0 + (NB == 2 ? (kk & 1u) * 8u : 0u); };
+    auto parity_of = [&](uint32_t kk) { return (NB == 2 ? kk >> 1 : kk) & 1u; };
 
     // Tile schedule.  Block b owns the tiles b, b + G, b + 2G, ... (G blocks in the grid, one or two per SM),
     // and its warps take them from a queue in shared memory as they become free.  A static share per WARP
@@ -673,12 +735,12 @@ step_kernel(const __grid_constant__ StepParams P) {
     };
     auto grab_tile = [&]() -> int {
         int li = 0;
-        if (lane == 0) li = atomicAdd(&queue_next, 1);
-        return tile_of(__shfl_sync(0xffffffffu, li, 0));
+        if (lane == 0) li = atom_add_s(queue, 1);
+        return tile_of(__reduce_max_sync(0xffffffffu, li));
     };
-    auto fetch_points = [&](int tile, int b) {   // lane 0 only
-        mbar_expect_tx(bar + b, tile_bytes);
-        bulk_load_hint(tile_buf(b), P.points + (size_t)tile * (size_t)(kTile * rowlen), tile_bytes, bar + b, pol_stream);
+    auto fetch_points = [&](int tile, uint32_t buf, uint32_t bar) {   // lane 0 only
+        mbar_expect_tx_s(bar, tile_bytes);
+        bulk_load_hint_s(buf, P.points + (size_t)tile * (size_t)(kTile * rowlen), tile_bytes, bar, pol_stream);
     };
 
     if (threadIdx.x == 0) {
@@ -695,8 +757,8 @@ step_kernel(const __grid_constant__ StepParams P) {
 #endif
     griddep_launch_dependents();            // the next step's grid may start taking free SM slots
     if (cur >= 0 && lane == 0) {
-        mbar_init(bar, 1);
-        if (NB == 2) mbar_init(bar + 1, 1);
+        mbar_init_s(bar0, 1);
+        if (NB == 2) mbar_init_s(bar0 + 8u, 1);
         mbar_init_fence();
     }
     griddep_wait();                         // ... but nothing touches the state before the previous step is complete
@@ -706,13 +768,11 @@ step_kernel(const __grid_constant__ StepParams P) {
         // previous launch's last block (visible here: griddepcontrol.wait orders after that grid's completion)
         unsigned long long step_index = 0ull;
         if (RAND) step_index = ld_volatile_u64(P.ctrl + kCtrlStep);
-        if (lane == 0) fetch_points(cur, 0);
+        if (lane == 0) fetch_points(cur, buf0, bar0);
         __syncwarp();
         TileScalars<J> sc;
         load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
         int nxt = grab_tile();
-        int b = 0;
-        uint32_t phase0 = 0, phase1 = 0;
         const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
 
         while (true) {
@@ -738,13 +798,13 @@ step_kernel(const __grid_constant__ StepParams P) {
             //    contents, tile i-1's observations, have long been read out by their bulk store)
             if (NB == 2 && nxt >= 0 && lane == 0) {
                 if (WOBS) bulk_wait_read0();
-                fetch_points(nxt, b ^ 1);
+                fetch_points(nxt, buf_of(k + 1u), bar_of(k + 1u));
             }
 
             // 4. objectives of the current tile: obs2 in place + catch mask
-            mbar_wait(bar + b, b ? phase1 : phase0);
-            if (b) phase1 ^= 1u; else phase0 ^= 1u;
-            float *row = tile_buf(b) + lane * rowlen;
+            const uint32_t buf_cur = buf_of(k);
+            mbar_wait_s(bar_of(k), parity_of(k));
+            const uint32_t row = buf_cur + (uint32_t)(lane * rowlen) * 4u;
             const uint32_t alive0 = sc.alive & amask;
             const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
             uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
@@ -814,8 +874,8 @@ step_kernel(const __grid_constant__ StepParams P) {
                         f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
                         f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
                         one_objective<true>(px, py, pz, f0, P.catch_tol, true);
-                        float *orow = tile_buf(b) + src * rowlen + lane * 3;
-                        orow[0] = px; orow[1] = py; orow[2] = pz;
+                        const uint32_t orow = buf_cur + (uint32_t)(src * rowlen + lane * 3) * 4u;
+                        sts_f(orow, px); sts_f(orow + 4, py); sts_f(orow + 8, pz);
                     }
                 }
             }
@@ -844,12 +904,12 @@ step_kernel(const __grid_constant__ StepParams P) {
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        bulk_store_hint(P.obs + (size_t)env0 * rowlen, tile_buf(b), tile_bytes, pol_stream);
+                        bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, buf_cur, tile_bytes, pol_stream);
                         bulk_commit();
                     }
                 } else if (valid) {
                     float *dst = P.obs + env * rowlen;
-                    for (int i = 0; i < rowlen; ++i) dst[i] = row[i];
+                    for (int i = 0; i < rowlen; ++i) dst[i] = lds_f(row + 4u * i);
                 }
             }
 
@@ -861,13 +921,13 @@ step_kernel(const __grid_constant__ StepParams P) {
                 __syncwarp();
                 if (lane == 0) {
                     if (WOBS) bulk_wait_read0();
-                    fetch_points(nxt, 0);
+                    fetch_points(nxt, buf0, bar0);
                 }
             }
             cur = nxt;
             nxt = grab_tile();
             sc = sn;
-            if (NB == 2) b ^= 1;
+            ++k;
             __syncwarp();
         }
         if (WOBS && lane == 0) bulk_wait_read0();   // shared memory must outlive the last bulk store's read

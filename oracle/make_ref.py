@@ -5,7 +5,7 @@
 
 The reference's hot path is one pure-Python module (``/root/reference/manytor.py``; numpy + stdlib, no
 build system), so "compiling it from the sources where they lie" is ``py_compile``: the output is
-``oracle/_ref/manytor.pyc`` -- CPython bytecode of the reference file, nothing edited, no source copied
+``oracle/_ref/manytor_ref.bin`` -- CPython bytecode (the content of a .pyc) of the reference file, nothing edited, no source copied
 into the repository.  ``oracle/_ref/`` is git-ignored (it stays out of history) but not gpurun-ignored,
 so it travels to the GPU box like the built ``.so``; there ``bench.py`` imports it (sourceless import)
 to time the reference's own ``Multienv`` loop (test_multi.py:11-34) on the host cores, and
@@ -24,7 +24,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.path.join(os.environ.get("MANYTOR_REFERENCE", "/root/reference"), "manytor.py")
 OUT_DIR = os.path.join(HERE, "_ref")
-OUT = os.path.join(OUT_DIR, "manytor.pyc")
+OUT = os.path.join(OUT_DIR, "manytor_ref.bin")    # CPython bytecode; not named *.pyc, which snapshot tools tend to skip
 META = os.path.join(OUT_DIR, "BUILD.json")
 
 
@@ -38,7 +38,7 @@ def build(verbose: bool = True) -> str | None:
         digest = hashlib.sha256(f.read()).hexdigest()
     with open(META, "w") as f:
         json.dump({"source": REF_SRC, "sha256": digest, "python": sys.version.split()[0],
-                   "recipe": "py_compile.compile(source, cfile='oracle/_ref/manytor.pyc')"}, f, indent=1)
+                   "recipe": "py_compile.compile(source, cfile='oracle/_ref/manytor_ref.bin')"}, f, indent=1)
     if verbose:
         print(f"oracle/_ref: byte-compiled {REF_SRC} (sha256 {digest[:12]}) -> {OUT}")
     return OUT

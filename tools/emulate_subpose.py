@@ -75,3 +75,31 @@ for name,z,err in (("rotation",zr,err_r),("reinsch",zq,err_q)):
     mism = neg!=neg_true
     print(f"{name}: max|dz| {err.max():.2e}  p99.9 {np.quantile(err,0.999):.2e}  mean {err.mean():.2e}  "
           f"flag mismatches {mism.sum()} / {N}  (max margin among mismatches {margin[mism].max() if mism.any() else 0:.2e})")
+
+# ---- round 2: two sub-poses per packed iteration (lane .x = odd k, lane .y = even k, both stepping 2*delta) ----
+sd1,cd1 = sc32(d[:,1]); sd2,cd2 = sc32(d[:,2]); sd3,cd3 = sc32(d[:,3])
+cdA = fma(cd1,cd3,-mul(sd1,sd3)); sdA = fma(sd1,cd3,mul(cd1,sd3))
+cdB = fma(cd1,cd3,mul(sd1,sd3));  sdB = fma(sd1,cd3,-mul(cd1,sd3))
+def init2(amp, cth, sth, sd, cd):
+    na = -mul(mul(f32(4),sd),sd)                       # -4 sin^2(delta): the step of both lanes is 2*delta
+    ax, ay = mul(amp,cth), mul(amp,sth)
+    x_m1 = fma(ax,cd,-mul(ay,sd))                      # amp cos(theta + delta)   (k = -1)
+    x_0 = ax                                           # k = 0
+    d_x = mul(mul(f32(2),ay),sd)                       # x(1) - x(-1) = 2 amp sin(theta) sin(delta)
+    d_y = fma(mul(ay,mul(f32(2),sd)),cd, mul(mul(f32(0.5),na),ax))   # x(2) - x(0) = amp (sin th sin 2d - 2 sin^2 d cos th)
+    return [x_m1,x_0],[d_x,d_y],na
+X1,D1,n1 = init2(f32(24.3),c1f,s1f,sd1,cd1)
+X2,D2,n2 = init2(f32(1.0),c2f,s2f,sd2,cd2)
+XA,DA,nA = init2(f32(13.5),cA,sA,sdA,cdA)
+XB,DB,nB = init2(f32(13.5),cB,sB,sdB,cdB)
+zp = np.empty((25,N),f32); zp[24]=zz(mul(f32(24.3),c1f), c2f, mul(f32(13.5),cA), mul(f32(13.5),cB))
+for it in range(12):
+    for lane in (0,1):
+        for X,D,n in ((X1,D1,n1),(X2,D2,n2),(XA,DA,nA),(XB,DB,nB)):
+            X[lane]=add(X[lane],D[lane]); D[lane]=fma(n,X[lane],D[lane])
+        k = 2*it+1+lane
+        zp[24-k]=zz(X1[lane],X2[lane],XA[lane],XB[lane])
+err_p = np.abs(zp.astype(np.float64)-ztrue).max(0)
+neg=(zp<0).any(0); mism = neg!=neg_true
+print(f"paired : max|dz| {err_p.max():.2e}  p99.9 {np.quantile(err_p,0.999):.2e}  mean {err_p.mean():.2e}  "
+      f"flag mismatches {mism.sum()} / {N}  (max margin among mismatches {margin[mism].max() if mism.any() else 0:.2e})")

@@ -54,6 +54,16 @@ c32 = horner32(cc, u)
 print("sin(pi r) fp32 max abs err", np.abs(s32 - np.sin(np.pi * r.astype(np.float64))).max())
 print("cos(pi r) fp32 max abs err", np.abs(c32 - np.cos(np.pi * r.astype(np.float64))).max())
 
+# ---- the same on |r| <= 0.5 (sincos_deg2's half-turn reduction: one sign flip instead of a quadrant fix-up) ----
+cs2, es2 = minimax_fit(sinc, 0.0, 0.25, 4)
+cc2, ec2 = minimax_fit(lambda u: np.cos(np.pi * np.sqrt(u)), 0.0, 0.25, 5)
+print("half-turn sin coef (u^0..):", [float(f32(c)) for c in cs2], "fit err", es2)
+print("half-turn cos coef (u^0..):", [float(f32(c)) for c in cc2], "fit err", ec2)
+r = np.linspace(-0.5, 0.5, 4000001).astype(f32)
+u = (r * r).astype(f32)
+print("half-turn sin(pi r) fp32 max abs err", np.abs((horner32(cs2, u) * r).astype(f32) - np.sin(np.pi * r.astype(np.float64))).max())
+print("half-turn cos(pi r) fp32 max abs err", np.abs(horner32(cc2, u) - np.cos(np.pi * r.astype(np.float64))).max())
+
 # ---- atan(t)/t in degrees as polynomial in s = t^2, t in [0,1] --------------
 def atd(s):
     t = np.sqrt(np.maximum(s, 1e-300))

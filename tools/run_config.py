@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run a few steps of one config (for ncu): python tools/run_config.py {ref|ur5|generic} [steps]"""
+"""Run a few steps of one config (for ncu): python tools/run_config.py {ref|ur5|generic} [steps] [other-build.so]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,12 +7,13 @@ from manytor_b200 import BatchedEnvs, UR5_ARM, REFERENCE_ARM
 which = sys.argv[1] if len(sys.argv) > 1 else "ref"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 n = 1 << 20
+lib = dict(lib_path=os.path.abspath(sys.argv[3])) if len(sys.argv) > 3 else {}
 if which == "ur5":
-    env = BatchedEnvs(n, 20, arm=UR5_ARM, device=0, auto_reset=True, horizon=1000, seed=3)
+    env = BatchedEnvs(n, 20, arm=UR5_ARM, device=0, auto_reset=True, horizon=1000, seed=3, **lib)
 elif which == "generic":
-    env = BatchedEnvs(n, 10, device=0, auto_reset=True, horizon=1000, seed=3, fk_mode=1)
+    env = BatchedEnvs(n, 10, device=0, auto_reset=True, horizon=1000, seed=3, fk_mode=1, **lib)
 else:
-    env = BatchedEnvs(n, 10, device=0, auto_reset=True, horizon=1000, seed=3)
+    env = BatchedEnvs(n, 10, device=0, auto_reset=True, horizon=1000, seed=3, **lib)
 env.reset()
 acts = torch.randint(-180, 180, (n, env.j), device="cuda").float()
 for _ in range(steps):
