@@ -1,6 +1,6 @@
 // fp32 math kernels of the step loop: degree-argument sin/cos, degree-valued
 // atan2 on the positive quadrant, Philox4x32-10.  Coefficients come from
-// tools/fit_polys.py (fp32 Horner error: sin/cos <= 9e-8 abs, atan <= 1.1e-5 deg).
+// tools/fit_polys.py (fp32 Horner error: sin/cos <= 1.6e-7 abs, atan2 <= 7.3e-5 deg).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -44,14 +44,13 @@ __device__ __forceinline__ float fast_rcp(float x) {
 __device__ __forceinline__ float atan2_deg_pos(float y, float x, float hyp) {
     float t = y * fast_rcp(fmaxf(x + hyp, 1e-30f));
     float s = t * t;
-    float p = -0.54776114f;
-    p = fmaf(p, s, 2.81390548f);
-    p = fmaf(p, s, -6.86439371f);
-    p = fmaf(p, s, 11.3934412f);
-    p = fmaf(p, s, -16.0764885f);
-    p = fmaf(p, s, 22.8855038f);
-    p = fmaf(p, s, -38.1957664f);
-    p = fmaf(p, s, 114.591545f);
+    float p = 0.917460918f;              // 2 atan(t) in degrees, degree 6 in s (tools/fit_polys.py: 7.3e-5 deg max error)
+    p = fmaf(p, s, -4.29046488f);
+    p = fmaf(p, s, 9.66606236f);
+    p = fmaf(p, s, -15.4837093f);
+    p = fmaf(p, s, 22.7891674f);
+    p = fmaf(p, s, -38.1899414f);
+    p = fmaf(p, s, 114.591492f);
     return p * t;
 }
 
@@ -124,17 +123,24 @@ __device__ __forceinline__ void sincos_deg_small2(float2 x, float2 &s, float2 &c
     c = cospi_poly2(u);
 }
 
+// one SMALL angle (|x| <= 45 degrees), scalar
+__device__ __forceinline__ void sincos_deg_small(float x, float &s, float &c) {
+    const float inv_hi = 0x1.6c16c2p-8f, inv_lo = -0x1.27d27ep-33f;
+    const float r = fmaf(x, inv_lo, x * inv_hi), u = r * r;
+    s = fmaf(fmaf(fmaf(-0.58907866f, u, 2.5497673f), u, -5.1677079f), u, 3.14159274f) * r;
+    c = fmaf(fmaf(fmaf(fmaf(0.23132971f, u, -1.33504462f), u, 4.05870724f), u, -4.93480206f), u, 1.0f);
+}
+
 // 2 atan(t) in degrees for two arguments in [0, 1] (the half-angle form of atan2_deg_pos)
 __device__ __forceinline__ float2 atan_half_deg2(float2 t) {
     float2 s = mul2(t, t);
-    float2 p = bc2(-0.54776114f);
-    p = fma2(p, s, bc2(2.81390548f));
-    p = fma2(p, s, bc2(-6.86439371f));
-    p = fma2(p, s, bc2(11.3934412f));
-    p = fma2(p, s, bc2(-16.0764885f));
-    p = fma2(p, s, bc2(22.8855038f));
-    p = fma2(p, s, bc2(-38.1957664f));
-    p = fma2(p, s, bc2(114.591545f));
+    float2 p = bc2(0.917460918f);
+    p = fma2(p, s, bc2(-4.29046488f));
+    p = fma2(p, s, bc2(9.66606236f));
+    p = fma2(p, s, bc2(-15.4837093f));
+    p = fma2(p, s, bc2(22.7891674f));
+    p = fma2(p, s, bc2(-38.1899414f));
+    p = fma2(p, s, bc2(114.591492f));
     return mul2(p, t);
 }
 

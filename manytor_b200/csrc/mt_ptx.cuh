@@ -130,6 +130,9 @@ __device__ __forceinline__ void st_hint(float4 *a, float4 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z),
                  "f"(v.w), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_hint(float2 *a, float2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1,%2}, %3;" ::"l"(a), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void st_hint(float *a, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
 }

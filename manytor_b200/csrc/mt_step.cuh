@@ -204,10 +204,11 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
             // combination u1 + (uA + uB) + cos(th2)(uA - uB) is packed as well: 14 instructions per two
             // sub-poses against 2 x 9.4.  Same error as the single-step recurrence (tools/emulate_subpose.py:
             // max |dz| 3.8e-5, no ground-flag flips in 4e5 steps).
-            float2 sd12, cd12, sd33, cd33;
+            float2 sd12, cd12;
+            float sd3, cd3;
             sincos_deg_small2(make_float2(d1, d2), sd12, cd12);
-            sincos_deg_small2(bc2(d3), sd33, cd33);
-            const float sd1 = sd12.x, cd1 = cd12.x, sd3 = sd33.x, cd3 = cd33.x;
+            sincos_deg_small(d3, sd3, cd3);
+            const float sd1 = sd12.x, cd1 = cd12.x;
             // A = th1 + th3, B = th1 - th3: cos/sin of the angles and of their steps by angle addition
             const float cA = fmaf(c1, c3, -(s1 * s3)), cB = fmaf(c1, c3, s1 * s3);
             const float sA = fmaf(s1, c3, c1 * s3), sB = fmaf(s1, c3, -(c1 * s3));
@@ -626,7 +627,15 @@ struct TileScalars {
     uint32_t cnt;     // ep_len in the wide layout
 };
 
-template <int J, bool RAND>
+// Where the episode length lives (StepParams::ep_shift): a compile-time objective count of at most 16 always
+// has it in the upper half of the alive word (mt_create), which removes the `counters` path, its register
+// and its selects from those kernels; otherwise the handle's choice is read at run time.
+template <int X>
+__device__ __forceinline__ int ep_shift_of(const StepParams &P) {
+    return (X > 0 && X <= 16) ? 16 : P.ep_shift;
+}
+
+template <int J, int X, bool RAND>
 __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, TileScalars<J> &s, uint64_t keep,
                                              uint64_t stream) {
     const size_t env = (size_t)env32;     // indices stay 32-bit in the kernel (n_envs < 2^31); one widening per address
@@ -639,6 +648,14 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
         s.g[1] = ld_hint(P.goals + env * 4 + 1, keep);
         float2 t = ld_hint(reinterpret_cast<const float2 *>(P.goals + env * 4 + 2), keep);
         s.g[2] = t.x; s.g[3] = t.y;
+    } else if (J % 2 == 0) {
+        // rows of J floats are 8-byte aligned: g[1] alone (g[0] stays unread, see above), then pairs
+        s.g[1] = ld_hint(P.goals + env * J + 1, keep);
+#pragma unroll
+        for (int i = 2; i < J; i += 2) {
+            const float2 t = ld_hint(reinterpret_cast<const float2 *>(P.goals + env * J + i), keep);
+            s.g[i] = t.x; s.g[i + 1] = t.y;
+        }
     } else {
 #pragma unroll
         for (int i = 1; i < J; ++i) s.g[i] = ld_hint(P.goals + env * J + i, keep);
@@ -650,6 +667,12 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
         } else if (J == 4) {
             float4 t = ld_hint(reinterpret_cast<const float4 *>(P.actions + env * 4), stream);
             s.a[0] = t.x; s.a[1] = t.y; s.a[2] = t.z; s.a[3] = t.w;
+        } else if (J % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < J; i += 2) {
+                const float2 t = ld_hint(reinterpret_cast<const float2 *>(P.actions + env * J + i), stream);
+                s.a[i] = t.x; s.a[i + 1] = t.y;
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < J; ++i) s.a[i] = ld_hint(P.actions + env * J + i, stream);
@@ -657,7 +680,7 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
     }
     s.alive = ld_hint(P.alive + env, keep);
     s.total = ld_hint(P.total_reward + env, keep);
-    s.cnt = P.ep_shift ? 0u : ld_hint(P.counters + env, keep);
+    s.cnt = ep_shift_of<X>(P) ? 0u : ld_hint(P.counters + env, keep);
 }
 
 // ---------------------------------------------------------------------------
@@ -771,9 +794,10 @@ step_kernel(const __grid_constant__ StepParams P) {
         if (lane == 0) fetch_points(cur, buf0, bar0);
         __syncwarp();
         TileScalars<J> sc;
-        load_scalars<J, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
+        load_scalars<J, X, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
         int nxt = grab_tile();
-        const uint32_t amask = P.ep_shift ? ((1u << P.ep_shift) - 1u) : 0xffffffffu;
+        const int ep_shift = ep_shift_of<X>(P);
+        const uint32_t amask = ep_shift ? ((1u << ep_shift) - 1u) : 0xffffffffu;
 
         while (true) {
             const int env0 = cur * kTile, env32 = env0 + lane;
@@ -783,7 +807,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 
             // 1. next tile's scalars on their way to registers
             TileScalars<J> sn;
-            if (nxt >= 0) load_scalars<J, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
+            if (nxt >= 0) load_scalars<J, X, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
             // 2. kinematics of the current tile (needs no objectives)
             if (RAND) draw_actions(P, step_index, P.env_id_base + env32, J, sc.a);
@@ -813,7 +837,7 @@ step_kernel(const __grid_constant__ StepParams P) {
             float rew = (alive1 != alive0) ? 1.0f : 0.0f;
             rew = neg ? -1.0f : rew;
             float total = sc.total + rew;
-            uint32_t eplen = min((P.ep_shift ? sc.alive >> P.ep_shift : sc.cnt) + 1u, P.ep_max);
+            uint32_t eplen = min((ep_shift ? sc.alive >> ep_shift : sc.cnt) + 1u, P.ep_max);
             ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
             bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
             bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
@@ -884,13 +908,17 @@ step_kernel(const __grid_constant__ StepParams P) {
             // 7. write back: state (coalesced), then the observation tile by one bulk store
             if (J == 4) {
                 st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(gn[0], gn[1], gn[2], gn[3]), pol_keep);
+            } else if (J % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < J; i += 2)
+                    st_hint(reinterpret_cast<float2 *>(P.goals + env * J + i), make_float2(gn[i], gn[i + 1]), pol_keep);
             } else {
 #pragma unroll
                 for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, gn[i], pol_keep);
             }
-            st_hint(P.alive + env, P.ep_shift ? (alive1 | (eplen << P.ep_shift)) : alive1, pol_keep);
+            st_hint(P.alive + env, ep_shift ? (alive1 | (eplen << ep_shift)) : alive1, pol_keep);
             st_hint(P.total_reward + env, total, pol_keep);
-            if (!P.ep_shift) st_hint(P.counters + env, eplen, pol_keep);
+            if (!ep_shift) st_hint(P.counters + env, eplen, pol_keep);
             if (valid) {
                 st_hint(P.reward + env, rew, pol_stream);
                 st_hint(P.done + env, done, pol_stream);
