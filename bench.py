@@ -376,23 +376,29 @@ def run_gpu(args) -> None:
     best_total = reps[order[0]][0]
 
     # ---- SURVEY config-3 protocol: in-kernel RNG actions, same repeats ---------------------------------
-    def rand_mode(write_obs):
-        g = None if args.no_graph else capture(lambda warm: env.rollout_random(3 if warm else K, write_obs=write_obs))
-        if g is not None:
-            g.replay()
-        out = []
-        for r in range(R):
-            env.rollout_random(W, write_obs=write_obs)
-            fence()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+    def rand_mode(write_obs, persistent):
+        """K x step(action_sample()) with in-kernel actions: as K launches of the step kernel, or as ONE launch of the
+        multi-step rollout kernel (a tile's state stays in registers, its objectives in shared memory, for all K steps)."""
+        os.environ["MT_ROLLOUT_PERSISTENT"] = "1" if persistent else "0"
+        try:
+            g = None if args.no_graph else capture(lambda warm: env.rollout_random(3 if warm else K, write_obs=write_obs))
             if g is not None:
                 g.replay()
-            else:
-                env.rollout_random(K, write_obs=write_obs)
-            e1.record(stream)
-            fence()
-            out.append(mtd.max_over_ranks(e0.elapsed_time(e1), dev))
+            out = []
+            for r in range(R):
+                env.rollout_random(W, write_obs=write_obs)
+                fence()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                if g is not None:
+                    g.replay()
+                else:
+                    env.rollout_random(K, write_obs=write_obs)
+                e1.record(stream)
+                fence()
+                out.append(mtd.max_over_ranks(e0.elapsed_time(e1), dev))
+        finally:
+            os.environ.pop("MT_ROLLOUT_PERSISTENT", None)
         out.sort()
         return out
 
@@ -405,10 +411,18 @@ def run_gpu(args) -> None:
                 "bytes_per_env_step": bytes_per, "hbm_gbs": n * K * bytes_per / (med_ms * 1e-3) / 1e9,
                 "frac_of_peak": n * K * bytes_per / (med_ms * 1e-3) / 1e9 / peak}
 
+    X3 = 12 * OBJ
     modes = {
-        "rollout_random_in_kernel_actions": mode_entry(rand_mode(True), env.bytes_per_env_step(False, True)),
-        "rollout_random_no_obs_write": mode_entry(rand_mode(False), env.bytes_per_env_step(False, False)),
+        "rollout_random_in_kernel_actions": mode_entry(rand_mode(True, False), env.bytes_per_env_step(False, True)),
+        "rollout_random_no_obs_write": mode_entry(rand_mode(False, False), env.bytes_per_env_step(False, False)),
+        # one launch for all K steps: per env-step only the outputs leave the SM (obs 12X + reward 4 + done 1), the
+        # state (24 B read + 24 B written) and the objectives (12X read) move once per K steps
+        "rollout_random_one_launch": mode_entry(rand_mode(True, True), X3 + 5 + (48 + X3) / K),
+        "rollout_random_one_launch_no_obs_write": mode_entry(rand_mode(False, True), 5 + (48 + X3) / K),
     }
+    for name in ("rollout_random_one_launch", "rollout_random_one_launch_no_obs_write"):
+        modes[name]["note"] = ("mt_rollout_random(K) as ONE launch of rollout_kernel; bound by instruction issue / the fp32 pipe, "
+                               "not by HBM: frac_of_peak is its (small) algorithmic traffic over the HBM peak")
     # the same steps as individual stream launches from Python (no graph)
     for i in range(W):
         step_fn(i)

@@ -681,42 +681,18 @@ static int check_ptr(const void *p, const char *name, bool required) {
     return MT_OK;
 }
 
-// launch the fused step kernel over tiles [t0, t1): a persistent grid sized to the SMs
-static int launch_step(mt_env *e, const float *actions, float *obs, float *reward, uint8_t *done, float *joints,
-                       bool rnd, long long t0, long long t1, cudaStream_t st, int ticket_slot = 0, bool advance = true) {
-    StepParams P = e->base;
-    P.actions = actions;
-    P.obs = obs;
-    P.reward = reward;
-    P.done = done;
-    P.joints = joints;
-    P.obj_stream = e->obj_stream;
-    P.obj_sets = e->obj_sets;
-    P.tile_begin = t0;
-    P.tile_end = t1;
-    // device-side bookkeeping done by the launch's last block (mt_step.cuh, epilogue)
-    P.ticket_slot = ticket_slot;
-    P.advance = advance ? 1 : 0;
-    P.launch_envs = ((t1 * kTile < e->n) ? t1 * kTile : e->n) - t0 * kTile;
-    const bool wobs = obs != nullptr;
-    const void *fn = nullptr;
-    if (e->jit) {
-        cudaKernel_t &k = e->jit_kernel[rnd ? 1 : 0][wobs ? 1 : 0];
-        if (!k) {                                             // other variants compile on first use
-            std::string err;
-            k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, rnd, wobs, err).kernel;
-            if (!k) return fail(MT_ERR_CUDA, "run-time specialisation failed: %s", err.c_str());
-        }
-        fn = (const void *)k;
-    } else {
-        fn = (const void *)pick_kernel(e->arm, e->cfg.n_obj, rnd, wobs);
-    }
-    if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
-    // Block shape: as many warps as ONE block can have on an SM (they share the block's tile queue), bounded
-    // by the kernel's __launch_bounds__ and by shared memory (nb tile buffers + nb mbarriers per warp);
-    // MT_WARPS_PER_BLOCK overrides the target (tuning / A-B runs).
-    const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
-    const size_t per_warp = nb * P.tile_bytes + nb * sizeof(uint64_t);
+// Block shape and grid of a persistent launch of `fn` over `tiles` tiles: as many warps as ONE block can have on
+// an SM (they share the block's tile queue), bounded by the kernel's __launch_bounds__ and by shared memory
+// (`per_warp` bytes each); MT_WARPS_PER_BLOCK overrides the target (tuning / A-B runs).  A launch with fewer
+// tiles than that x SMs (small shards, the chunks of mt_step_host) uses smaller blocks, several per SM, so that
+// it still spreads over every SM.
+struct LaunchShape {
+    int wpb = 0;
+    unsigned grid = 0;
+    size_t smem = 0;
+};
+
+static int plan_launch(mt_env *e, const void *fn, size_t per_warp, long long tiles, LaunchShape &out) {
     int max_wpb = 0;
     auto hit = e->block_shape.find(fn);
     if (hit != e->block_shape.end()) {
@@ -737,9 +713,6 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
         if (per_sm < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (%d warps, %zu B of shared memory)", max_wpb, smem_max);
         e->block_shape[fn] = max_wpb;
     }
-    // A launch with fewer tiles than max_wpb x SMs (small shards, the chunks of mt_step_host) uses smaller
-    // blocks, several per SM, so that it still spreads over every SM.
-    const long long tiles = t1 - t0;
     long long fair = (tiles + e->num_sms - 1) / e->num_sms;
     const int wpb = (int)(fair < 1 ? 1 : (fair > max_wpb ? max_wpb : fair));
     int per_sm = 1;                                               // blocks of this shape one SM can hold
@@ -754,15 +727,20 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
             e->occupancy[key] = per_sm;
         }
     }
-    const size_t smem = (size_t)wpb * per_warp;
     const long long want = (tiles + wpb - 1) / wpb;
     const long long cap = (long long)per_sm * e->num_sms;
-    const unsigned grid = (unsigned)(want < cap ? want : cap);
-    // programmatic dependent launch: see griddep_wait() in mt_ptx.cuh
+    out.wpb = wpb;
+    out.grid = (unsigned)(want < cap ? want : cap);
+    out.smem = (size_t)wpb * per_warp;
+    return MT_OK;
+}
+
+// programmatic dependent launch: see griddep_wait() in mt_ptx.cuh
+static int launch_pdl(const void *fn, const LaunchShape &shape, const StepParams &P, cudaStream_t st) {
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(wpb * kTile);
-    lc.dynamicSmemBytes = smem;
+    lc.gridDim = dim3(shape.grid);
+    lc.blockDim = dim3(shape.wpb * kTile);
+    lc.dynamicSmemBytes = shape.smem;
     lc.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -771,7 +749,97 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     lc.numAttrs = 1;
     void *args[] = {(void *)&P};
     CU(cudaLaunchKernelExC(&lc, fn, args));
+    return MT_OK;
+}
+
+// launch the fused step kernel over tiles [t0, t1): a persistent grid sized to the SMs
+static int launch_step(mt_env *e, const float *actions, float *obs, float *reward, uint8_t *done, float *joints,
+                       bool rnd, long long t0, long long t1, cudaStream_t st, int ticket_slot = 0, bool advance = true) {
+    StepParams P = e->base;
+    P.actions = actions;
+    P.obs = obs;
+    P.reward = reward;
+    P.done = done;
+    P.joints = joints;
+    P.obj_stream = e->obj_stream;
+    P.obj_sets = e->obj_sets;
+    P.tile_begin = t0;
+    P.tile_end = t1;
+    // device-side bookkeeping done by the launch's last block (mt_step.cuh, block_epilogue)
+    P.ticket_slot = ticket_slot;
+    P.advance = advance ? 1 : 0;
+    P.n_steps = 1;
+    P.launch_envs = ((t1 * kTile < e->n) ? t1 * kTile : e->n) - t0 * kTile;
+    const bool wobs = obs != nullptr;
+    const void *fn = nullptr;
+    if (e->jit) {
+        cudaKernel_t &k = e->jit_kernel[rnd ? 1 : 0][wobs ? 1 : 0];
+        if (!k) {                                             // other variants compile on first use
+            std::string err;
+            k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, rnd, wobs, err).kernel;
+            if (!k) return fail(MT_ERR_CUDA, "run-time specialisation failed: %s", err.c_str());
+        }
+        fn = (const void *)k;
+    } else {
+        fn = (const void *)pick_kernel(e->arm, e->cfg.n_obj, rnd, wobs);
+    }
+    if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
+    const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
+    LaunchShape shape;
+    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + nb * sizeof(uint64_t), t1 - t0, shape)) return rc;
+    if (int rc = launch_pdl(fn, shape, P, st)) return rc;
     e->launches++;
+    return MT_OK;
+}
+
+// Multi-step random rollout in ONE launch (rollout_kernel, mt_step.cuh): built-in arms only; handles whose step
+// kernels come from NVRTC, and run-time DH tables, take the per-step launches instead (returns false).
+template <int ARM>
+static StepFn pick_rollout_x(int x, bool wobs) {
+    switch (x) {
+        case 10: return wobs ? rollout_kernel<ARM, 10, true> : rollout_kernel<ARM, 10, false>;
+        case 20: return wobs ? rollout_kernel<ARM, 20, true> : rollout_kernel<ARM, 20, false>;
+        default: return wobs ? rollout_kernel<ARM, 0, true> : rollout_kernel<ARM, 0, false>;
+    }
+}
+
+static StepFn pick_rollout(int arm, int x, bool wobs) {
+    switch (arm) {
+        case 0: return pick_rollout_x<0>(x, wobs);
+#define MT_PICK(ID) case ID: return pick_rollout_x<ID>(x, wobs);
+        MT_FOR_EACH_PRESET_ARM(MT_PICK)
+#undef MT_PICK
+    }
+    return nullptr;
+}
+
+static int launch_rollout(mt_env *e, int n_steps, float *obs, float *reward, uint8_t *done, cudaStream_t st, bool &launched) {
+    launched = false;
+    if (e->jit || n_steps < 2) return MT_OK;
+    if (const char *v = std::getenv("MT_ROLLOUT_PERSISTENT"))
+        if (v[0] == '0') return MT_OK;
+    const void *fn = (const void *)pick_rollout(e->arm, e->cfg.n_obj, obs != nullptr);
+    if (!fn) return MT_OK;
+    StepParams P = e->base;
+    P.actions = nullptr;
+    P.obs = obs;
+    P.reward = reward;
+    P.done = done;
+    P.joints = nullptr;
+    P.obj_stream = e->obj_stream;
+    P.obj_sets = e->obj_sets;
+    P.tile_begin = 0;
+    P.tile_end = e->n_tiles;
+    P.ticket_slot = 0;
+    P.advance = n_steps;
+    P.n_steps = n_steps;
+    P.launch_envs = e->n * (long long)n_steps;
+    const size_t nb = obs ? 2 : 1;                            // objectives (+ observations) per warp, one barrier
+    LaunchShape shape;
+    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + sizeof(uint64_t), e->n_tiles, shape)) return rc;
+    if (int rc = launch_pdl(fn, shape, P, st)) return rc;
+    e->launches++;
+    launched = true;
     return MT_OK;
 }
 
@@ -872,8 +940,17 @@ extern "C" int mt_rollout_random(mt_env *e, int32_t n_steps, float *obs_dev, flo
     }
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = timing_begin(e, st))) return rc;
-    for (int s = 0; s < n_steps; ++s) {
-        if ((rc = launch_step(e, nullptr, obs_dev, reward_dev, done_dev, nullptr, true, 0, e->n_tiles, st))) return rc;
+    // chunks of at most 4096 steps per launch keep a launch's work bounded (a tile's warp holds it for the chunk)
+    for (int s = 0; s < n_steps;) {
+        const int chunk = n_steps - s < 4096 ? n_steps - s : 4096;
+        bool launched = false;
+        if ((rc = launch_rollout(e, chunk, obs_dev, reward_dev, done_dev, st, launched))) return rc;
+        if (launched) {
+            s += chunk;
+        } else {
+            if ((rc = launch_step(e, nullptr, obs_dev, reward_dev, done_dev, nullptr, true, 0, e->n_tiles, st))) return rc;
+            ++s;
+        }
     }
     return timing_end(e, st);
 }

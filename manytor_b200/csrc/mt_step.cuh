@@ -73,7 +73,8 @@ struct StepParams {
     long long env_id_base;
     uint32_t seed_lo, seed_hi;
     int32_t ticket_slot;       // which ticket this launch uses (launches that may overlap in time use different ones)
-    int32_t advance;           // 1: this launch completes a step -> its last block increments the step index
+    int32_t advance;           // steps this launch completes: its last block adds them to the step index
+    int32_t n_steps;           // rollout_kernel: steps per launch
     long long launch_envs;     // envs this launch advances (added to the env-step count by its last block)
     int32_t n_obj, n_joints, substeps, horizon, flags, obj_sets;
     int32_t action_low;
@@ -207,7 +208,11 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
             float2 sd12, cd12;
             float sd3, cd3;
             sincos_deg_small2(make_float2(d1, d2), sd12, cd12);
+#ifdef MT_V_D3PACKED
+            { float2 s33, c33; sincos_deg_small2(bc2(d3), s33, c33); sd3 = s33.x; cd3 = c33.x; }
+#else
             sincos_deg_small(d3, sd3, cd3);
+#endif
             const float sd1 = sd12.x, cd1 = cd12.x;
             // A = th1 + th3, B = th1 - th3: cos/sin of the angles and of their steps by angle addition
             const float cA = fmaf(c1, c3, -(s1 * s3)), cB = fmaf(c1, c3, s1 * s3);
@@ -532,10 +537,11 @@ __device__ __forceinline__ uint32_t pair_objective(float2 PX, float2 PY, float2 
     return (c0 ? 1u : 0u) | (c1 ? 2u : 0u);
 }
 
-// Walk one env's row of objectives in shared memory (`row` = its shared-space byte address),
-// observations written back in place.  Returns the bitmask of objectives inside the catch cube.
+// Walk one env's row of objectives in shared memory (`row` = its shared-space byte address); the
+// observations go to `orow` -- the same row for the step kernel (in place), another buffer for the
+// multi-step rollout, which keeps the objectives.  Returns the bitmask of objectives inside the catch cube.
 template <int X, bool WOBS>
-__device__ __forceinline__ uint32_t walk_row(uint32_t row, int x, const Frames &f, float tol, uint32_t alive) {
+__device__ __forceinline__ uint32_t walk_row(uint32_t row, uint32_t orow, int x, const Frames &f, float tol, uint32_t alive) {
     uint32_t caught = 0;
     const int xx = X ? X : x;
     if ((xx & 1) == 0) {
@@ -549,9 +555,10 @@ __device__ __forceinline__ uint32_t walk_row(uint32_t row, int x, const Frames &
                                                     (alive >> (2 * pr + 1)) & 1u, o);
             caught |= c << (2 * pr);
             if (WOBS) {
-                sts_f2(q, make_float2(o[0], o[1]));
-                sts_f2(q + 8, make_float2(o[2], o[3]));
-                sts_f2(q + 16, make_float2(o[4], o[5]));
+                const uint32_t w = orow + pr * 24;
+                sts_f2(w, make_float2(o[0], o[1]));
+                sts_f2(w + 8, make_float2(o[2], o[3]));
+                sts_f2(w + 16, make_float2(o[4], o[5]));
             }
         }
     } else {
@@ -570,14 +577,14 @@ __device__ __forceinline__ uint32_t walk_row(uint32_t row, int x, const Frames &
             caught |= c << pt;
             if (WOBS) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) sts_f(q + 4 * k, o[k]);
+                for (int k = 0; k < 6; ++k) sts_f(orow + pt * 12 + 4 * k, o[k]);
             }
         }
         const uint32_t q = row + pt * 12;
         float px = lds_f(q), py = lds_f(q + 4), pz = lds_f(q + 8);
         const bool c = one_objective<WOBS>(px, py, pz, f, tol, (alive >> pt) & 1u);
         caught |= c ? (1u << pt) : 0u;
-        if (WOBS) { sts_f(q, px); sts_f(q + 4, py); sts_f(q + 8, pz); }
+        if (WOBS) { const uint32_t w = orow + pt * 12; sts_f(w, px); sts_f(w + 4, py); sts_f(w + 8, pz); }
     }
     return caught;
 }
@@ -618,13 +625,13 @@ __device__ __forceinline__ void draw_actions(const StepParams &P, unsigned long 
     }
 }
 
-// Per-env scalars of one tile, prefetched into registers one tile ahead.
+// Per-env pose and action of one tile, prefetched into registers one tile ahead (the kinematics need them
+// first).  The other two state words (alive | episode length, total reward) are only needed after the
+// kinematics, so they are loaded at the top of their own tile's iteration -- the ~450 instructions of
+// kinematics per warp cover the latency -- instead of living in registers for a whole tile as well.
 template <int J>
 struct TileScalars {
     float g[J], a[J];
-    uint32_t alive;   // the state word: alive mask (| ep_len << ep_shift in the packed layout)
-    float total;
-    uint32_t cnt;     // ep_len in the wide layout
 };
 
 // Where the episode length lives (StepParams::ep_shift): a compile-time objective count of at most 16 always
@@ -632,7 +639,11 @@ struct TileScalars {
 // and its selects from those kernels; otherwise the handle's choice is read at run time.
 template <int X>
 __device__ __forceinline__ int ep_shift_of(const StepParams &P) {
+#ifdef MT_V_EPRUNTIME
+    return P.ep_shift;
+#else
     return (X > 0 && X <= 16) ? 16 : P.ep_shift;
+#endif
 }
 
 template <int J, int X, bool RAND>
@@ -678,9 +689,123 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
             for (int i = 0; i < J; ++i) s.a[i] = ld_hint(P.actions + env * J + i, stream);
         }
     }
-    s.alive = ld_hint(P.alive + env, keep);
-    s.total = ld_hint(P.total_reward + env, keep);
-    s.cnt = ep_shift_of<X>(P) ? 0u : ld_hint(P.counters + env, keep);
+}
+
+// ---------------------------------------------------------------------------
+// What a step does to one env once its kinematics and objective walk are done (per lane, warp-converged):
+// reward / done (manytor.py:205-212, 258-259, 170-171), the block's statistics, and the auto-reset with
+// objective refresh (manytor.py:219-241; test_single.py:20-21,32).
+//   in : neg (ground flag), alive0 / caught (masks), a (the action = new goals), total / eplen (before this step)
+//   out: gn (goals after the step), total, alive1, eplen (after the step and a possible reset), rew, done
+//   obs_buf   shared-space address of the tile's observations (first observation of a new episode goes there
+//             when obs_after_reset is set)
+//   pts_buf   shared-space address of a resident copy of the tile's objectives to refresh as well, or 0
+// Resets are rare (one env-step in ~550 for random actions), so the warp handles its ending envs one at a
+// time and COOPERATIVELY: lane p draws objective p (x <= 32 lanes busy) instead of the one ending lane
+// drawing all x while 31 lanes idle.
+// ---------------------------------------------------------------------------
+template <int J, bool WOBS>
+__device__ __forceinline__ void settle_step(const StepParams &P, int lane, int env0, bool valid, int x, int rowlen, bool neg,
+                                            uint32_t alive0, uint32_t caught, const float *a, float *gn, float &total,
+                                            uint32_t &alive1, uint32_t &eplen, float &rew, uint8_t &done,
+                                            uint32_t &ground_steps, unsigned long long *blk_stat, uint32_t obs_buf,
+                                            uint32_t pts_buf) {
+    alive1 = alive0 & ~caught;                                             // manytor.py:168
+    rew = (alive1 != alive0) ? 1.0f : 0.0f;
+    rew = neg ? -1.0f : rew;
+    total += rew;
+    eplen = min(eplen + 1u, P.ep_max);
+    ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
+    const bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
+    const bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
+    done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
+#pragma unroll
+    for (int i = 0; i < J; ++i) gn[i] = a[i];                              // goals <- action (manytor.py:184)
+    const bool ending = ((P.flags & kAutoReset) != 0) & (done != 0) & valid;
+    uint32_t pending = __ballot_sync(0xffffffffu, ending);
+    if (pending) {                                                         // warp-uniform, rare
+        // fold the ending episodes into the block's statistics: one warp reduction per word and one
+        // shared-memory atomic from lane 0 (five same-address GLOBAL atomics per ending env in round 1)
+        const uint32_t n_term = __popc(__ballot_sync(0xffffffffu, ending & term));
+        const int r_sum = __reduce_add_sync(0xffffffffu, ending ? (int)total : 0);
+        const uint32_t l_sum = __reduce_add_sync(0xffffffffu, ending ? eplen : 0u);
+        const uint32_t c_sum = __reduce_add_sync(0xffffffffu, ending ? (uint32_t)(x - __popc(alive1)) : 0u);
+        if (lane == 0) {
+            atomicAdd(&blk_stat[0], (unsigned long long)__popc(pending));
+            atomicAdd(&blk_stat[1], (unsigned long long)n_term);
+            atomicAdd(&blk_stat[2], (unsigned long long)(long long)r_sum);
+            atomicAdd(&blk_stat[3], (unsigned long long)l_sum);
+            atomicAdd(&blk_stat[4], (unsigned long long)c_sum);
+        }
+    }
+    if (ending) {
+#pragma unroll
+        for (int i = 0; i < J; ++i) gn[i] = 0.f;
+        alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
+        total = 0.f;
+        eplen = 0u;
+    }
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1u;
+        const size_t renv = (size_t)(env0 + src);
+        const uint32_t ep = P.episode[renv];                               // resets so far (broadcast load)
+        __syncwarp();
+        if (lane == src) P.episode[renv] = ep + 1u;
+        if (lane < x) {
+            float px, py, pz;
+            if (P.obj_stream) {
+                const float *srcp = P.obj_stream + (((size_t)(ep % (uint32_t)P.obj_sets) * (size_t)P.n + renv) * x + lane) * 3;
+                px = srcp[0]; py = srcp[1]; pz = srcp[2];
+            } else {
+                sample_point(P, P.env_id_base + (long long)renv, ep, lane, px, py, pz);
+            }
+            const bool pair = (x & 1) == 0;
+            float *grow = P.points + renv * rowlen;
+            grow[point_index(pair, lane, 0)] = px;
+            grow[point_index(pair, lane, 1)] = py;
+            grow[point_index(pair, lane, 2)] = pz;
+            if (pts_buf) {
+                const uint32_t prow = pts_buf + (uint32_t)(src * rowlen) * 4u;
+                sts_f(prow + 4u * point_index(pair, lane, 0), px);
+                sts_f(prow + 4u * point_index(pair, lane, 1), py);
+                sts_f(prow + 4u * point_index(pair, lane, 2), pz);
+            }
+            if (WOBS && (P.flags & kObsAfterReset)) {
+                Frames f0;
+                f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
+                f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
+                one_objective<true>(px, py, pz, f0, P.catch_tol, true);
+                const uint32_t orow = obs_buf + (uint32_t)(src * rowlen + lane * 3) * 4u;
+                sts_f(orow, px); sts_f(orow + 4, py); sts_f(orow + 8, pz);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// Warp -> block -> device bookkeeping at the end of a launch: every warp adds its ground-contact count to the
+// block's shared-memory accumulators; the block's last warp flushes them with one atomic per non-zero word;
+// the launch's last block (ticket) adds the launch's env-steps and advances the step index by `P.advance`.
+__device__ __forceinline__ void block_epilogue(const StepParams &P, int lane, int wpb, uint32_t ground_steps,
+                                               unsigned long long *blk_stat, unsigned int *warps_done) {
+    if (lane != 0) return;
+    if (ground_steps) atomicAdd(&blk_stat[5], (unsigned long long)ground_steps);
+    __threadfence_block();
+    if (atomicAdd(warps_done, 1u) != (unsigned)wpb - 1u) return;
+    __threadfence_block();
+#pragma unroll
+    for (int k = 0; k < kBlockStats; ++k) {
+        const unsigned long long v = reinterpret_cast<volatile unsigned long long *>(blk_stat)[k];
+        if (v) atomicAdd(P.stats + 1 + k, v);
+    }
+    __threadfence();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(P.ctrl + kCtrlTicket + P.ticket_slot);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+        atomicExch(ticket, 0u);
+        atomicAdd(P.stats, (unsigned long long)P.launch_envs);
+        if (P.advance) atomicAdd(P.ctrl + kCtrlStep, (unsigned long long)P.advance);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -805,7 +930,10 @@ step_kernel(const __grid_constant__ StepParams P) {
             const bool full = env0 + kTile <= n_envs;  // warp-uniform
             const bool valid = env32 < n_envs;
 
-            // 1. next tile's scalars on their way to registers
+            // 1. this tile's state words and the next tile's pose / action on their way to registers
+            const uint32_t word = ld_hint(P.alive + env, pol_keep);          // alive mask (| ep_len << ep_shift when packed)
+            float total = ld_hint(P.total_reward + env, pol_keep);
+            uint32_t eplen = ep_shift ? 0u : ld_hint(P.counters + env, pol_keep);
             TileScalars<J> sn;
             if (nxt >= 0) load_scalars<J, X, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
@@ -829,81 +957,16 @@ step_kernel(const __grid_constant__ StepParams P) {
             const uint32_t buf_cur = buf_of(k);
             mbar_wait_s(bar_of(k), parity_of(k));
             const uint32_t row = buf_cur + (uint32_t)(lane * rowlen) * 4u;
-            const uint32_t alive0 = sc.alive & amask;
-            const uint32_t caught = walk_row<X, WOBS>(row, x, f, P.catch_tol, alive0);
-            uint32_t alive1 = alive0 & ~caught;                                // manytor.py:168
+            const uint32_t alive0 = word & amask;
+            const uint32_t caught = walk_row<X, WOBS>(row, row, x, f, P.catch_tol, alive0);
 
-            // 5. reward / done (manytor.py:205-212, 258-259, 170-171)
-            float rew = (alive1 != alive0) ? 1.0f : 0.0f;
-            rew = neg ? -1.0f : rew;
-            float total = sc.total + rew;
-            uint32_t eplen = min((ep_shift ? sc.alive >> ep_shift : sc.cnt) + 1u, P.ep_max);
-            ground_steps += __popc(__ballot_sync(0xffffffffu, neg & valid));
-            bool term = (alive1 == 0u) | (((P.flags & kTerminateOnGround) != 0) & neg);
-            bool trunc = (P.horizon > 0) & (eplen >= (uint32_t)P.horizon) & !term;
-            const uint8_t done = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0));
-
-            // 6. auto-reset with objective refresh (manytor.py:219-241; test_single.py:20-21,32).
-            //    Rare (one env-step in ~550 for random actions), so the warp handles its ending envs
-            //    one at a time and COOPERATIVELY: lane p draws objective p (x <= 32 lanes busy) instead
-            //    of the one ending lane drawing all x while 31 lanes idle.
-            float gn[J];
-#pragma unroll
-            for (int i = 0; i < J; ++i) gn[i] = sc.a[i];                      // goals <- action (manytor.py:184)
-            const bool ending = ((P.flags & kAutoReset) != 0) & (done != 0) & valid;
-            uint32_t pending = __ballot_sync(0xffffffffu, ending);
-            if (pending) {                                                     // warp-uniform, rare
-                // fold the ending episodes into the block's statistics: one warp reduction per word and one
-                // shared-memory atomic from lane 0 (five same-address GLOBAL atomics per ending env before)
-                const uint32_t n_term = __popc(__ballot_sync(0xffffffffu, ending & term));
-                const int r_sum = __reduce_add_sync(0xffffffffu, ending ? (int)total : 0);
-                const uint32_t l_sum = __reduce_add_sync(0xffffffffu, ending ? eplen : 0u);
-                const uint32_t c_sum = __reduce_add_sync(0xffffffffu, ending ? (uint32_t)(x - __popc(alive1)) : 0u);
-                if (lane == 0) {
-                    atomicAdd(&blk_stat[0], (unsigned long long)__popc(pending));
-                    atomicAdd(&blk_stat[1], (unsigned long long)n_term);
-                    atomicAdd(&blk_stat[2], (unsigned long long)(long long)r_sum);
-                    atomicAdd(&blk_stat[3], (unsigned long long)l_sum);
-                    atomicAdd(&blk_stat[4], (unsigned long long)c_sum);
-                }
-            }
-            if (ending) {
-#pragma unroll
-                for (int i = 0; i < J; ++i) gn[i] = 0.f;
-                alive1 = (x >= 32) ? 0xffffffffu : ((1u << x) - 1u);
-                total = 0.f;
-                eplen = 0u;
-            }
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1u;
-                const size_t renv = (size_t)(env0 + src);
-                const uint32_t ep = P.episode[renv];                           // resets so far (broadcast load)
-                __syncwarp();
-                if (lane == src) P.episode[renv] = ep + 1u;
-                if (lane < x) {
-                    float px, py, pz;
-                    if (P.obj_stream) {
-                        const float *srcp = P.obj_stream + (((size_t)(ep % (uint32_t)P.obj_sets) * (size_t)P.n + renv) * x + lane) * 3;
-                        px = srcp[0]; py = srcp[1]; pz = srcp[2];
-                    } else {
-                        sample_point(P, P.env_id_base + (long long)renv, ep, lane, px, py, pz);
-                    }
-                    float *grow = P.points + renv * rowlen;
-                    grow[point_index((x & 1) == 0, lane, 0)] = px;
-                    grow[point_index((x & 1) == 0, lane, 1)] = py;
-                    grow[point_index((x & 1) == 0, lane, 2)] = pz;
-                    if (WOBS && (P.flags & kObsAfterReset)) {
-                        Frames f0;
-                        f0.anchor[0] = P.zero_anchor[0]; f0.anchor[1] = P.zero_anchor[1]; f0.anchor[2] = P.zero_anchor[2];
-                        f0.catcher[0] = f0.catcher[1] = f0.catcher[2] = 3.0e38f;
-                        one_objective<true>(px, py, pz, f0, P.catch_tol, true);
-                        const uint32_t orow = buf_cur + (uint32_t)(src * rowlen + lane * 3) * 4u;
-                        sts_f(orow, px); sts_f(orow + 4, py); sts_f(orow + 8, pz);
-                    }
-                }
-            }
-            __syncwarp();
+            // 5-6. reward / done, statistics, auto-reset with objective refresh
+            float gn[J], rew;
+            uint32_t alive1;
+            uint8_t done;
+            if (ep_shift) eplen = word >> ep_shift;
+            settle_step<J, WOBS>(P, lane, env0, valid, x, rowlen, neg, alive0, caught, sc.a, gn, total, alive1, eplen, rew, done,
+                                 ground_steps, blk_stat, buf_cur, 0u);
 
             // 7. write back: state (coalesced), then the observation tile by one bulk store
             if (J == 4) {
@@ -970,27 +1033,138 @@ step_kernel(const __grid_constant__ StepParams P) {
         }
     }
 #endif
-    // Epilogue.  Warp -> block: shared-memory accumulators; the block's last warp -> device: one atomic per
-    // non-zero word; the launch's last block (ticket) -> the env-step count and the step index.
-    if (lane == 0) {
-        if (ground_steps) atomicAdd(&blk_stat[5], (unsigned long long)ground_steps);
-        __threadfence_block();
-        if (atomicAdd(&warps_done, 1u) == (unsigned)wpb - 1u) {
-            __threadfence_block();
+    block_epilogue(P, lane, wpb, ground_steps, blk_stat, &warps_done);
+}
+
+
+// ---------------------------------------------------------------------------
+// Multi-step random rollout: n_steps x step(action_sample()) in ONE launch (mt_rollout_random).
+//
+// A tile's step t + 1 depends only on its own step t, so the warp that takes a tile keeps it for all
+// P.n_steps steps: pose, alive word and total reward stay in registers, the objectives stay in shared memory
+// (fetched once per tile by one TMA bulk copy; a reset refreshes the row in place), and only what a step
+// PRODUCES leaves the SM every step -- observations (one bulk store per tile and step, from a second buffer),
+// reward, done.  Against n_steps launches of step_kernel<.., RAND = true, ..> this removes, per env-step, the
+// read and write of the state (48 B), the read of the objectives (12 X B) and every launch boundary with its
+// staggered start and drain; results are bit-identical (same arithmetic, same action stream: step index of
+// the launch + s).  Algorithmic bytes per env-step: 12 X + 5 written, plus (48 + 12 X) / n_steps.
+// ---------------------------------------------------------------------------
+template <int ARM, int X, bool WOBS>
+__global__ void __launch_bounds__(((ARM == 0) ? kMaxWarpsRefArm : kMaxWarpsGeneric) * kTile, 1)
+rollout_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int queue_next;
+    __shared__ unsigned int warps_done;
+    __shared__ unsigned long long blk_stat[kBlockStats];
+    constexpr int J = ArmJoints<ARM>::value;
+    constexpr int NB = WOBS ? 2 : 1;                      // objectives (+ observations) of the warp's tile
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int warp = __reduce_max_sync(0xffffffffu, (int)(threadIdx.x >> 5));
+    const int x = X ? X : P.n_obj;
+    const int rowlen = 3 * x;
+    const uint32_t tile_bytes = (uint32_t)(kTile * rowlen * 4);
+    const uint32_t sbase = smem_addr(smem);
+    const uint32_t pts = sbase + (uint32_t)(NB * warp) * P.tile_bytes, obuf = pts + P.tile_bytes;
+    const uint32_t bar = sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)warp * 8u;
+    const uint32_t queue = smem_addr(&queue_next);
+    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
+    const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
+    auto tile_of = [&](int li) -> int {
+        const int t = tile_begin + li * (int)gridDim.x + (int)blockIdx.x;
+        return t < tile_end ? t : -1;
+    };
+    if (threadIdx.x == 0) {
+        queue_next = wpb;
+        warps_done = 0u;
 #pragma unroll
-            for (int k = 0; k < kBlockStats; ++k) {
-                const unsigned long long v = reinterpret_cast<volatile unsigned long long *>(blk_stat)[k];
-                if (v) atomicAdd(P.stats + 1 + k, v);
-            }
-            __threadfence();
-            unsigned int *ticket = reinterpret_cast<unsigned int *>(P.ctrl + kCtrlTicket + P.ticket_slot);
-            if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
-                atomicExch(ticket, 0u);
-                atomicAdd(P.stats, (unsigned long long)P.launch_envs);
-                if (P.advance) atomicAdd(P.ctrl + kCtrlStep, 1ull);
-            }
-        }
+        for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
     }
+    __syncthreads();
+    int cur = tile_of(warp);
+    griddep_launch_dependents();
+    if (cur >= 0 && lane == 0) {
+        mbar_init_s(bar, 1);
+        mbar_init_fence();
+    }
+    griddep_wait();
+    uint32_t ground_steps = 0;
+    if (cur >= 0) {
+        const unsigned long long step0 = ld_volatile_u64(P.ctrl + kCtrlStep);
+        const int ep_shift = ep_shift_of<X>(P);
+        const uint32_t amask = ep_shift ? ((1u << ep_shift) - 1u) : 0xffffffffu;
+        const uint32_t row = pts + (uint32_t)(lane * rowlen) * 4u, orow = obuf + (uint32_t)(lane * rowlen) * 4u;
+        for (uint32_t k = 0; cur >= 0; ++k) {
+            const int env0 = cur * kTile, env32 = env0 + lane;
+            const size_t env = (size_t)env32;
+            const bool full = env0 + kTile <= n_envs, valid = env32 < n_envs;
+            if (lane == 0) {                               // objectives: HBM -> shared, once for all the steps
+                mbar_expect_tx_s(bar, tile_bytes);
+                bulk_load_hint_s(pts, P.points + (size_t)cur * (size_t)(kTile * rowlen), tile_bytes, bar, pol_stream);
+            }
+            TileScalars<J> sc;
+            load_scalars<J, X, true>(P, env32, sc, pol_keep, pol_stream);
+            uint32_t alive = ld_hint(P.alive + env, pol_keep);
+            float total = ld_hint(P.total_reward + env, pol_keep);
+            uint32_t eplen = ep_shift ? 0u : ld_hint(P.counters + env, pol_keep);
+            if (ep_shift) { eplen = alive >> ep_shift; alive &= amask; }
+            float rew = 0.f;
+            uint8_t done = 0;
+            for (int s = 0; s < P.n_steps; ++s) {
+                draw_actions(P, step0 + (unsigned long long)s, P.env_id_base + env32, J, sc.a);
+                Frames f;
+                if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, nullptr);
+                else generic_arm<ARM>(P, sc.g, sc.a, f, nullptr);
+                const bool neg = f.zmin < 0.0f;
+                if (s == 0) mbar_wait_s(bar, k & 1u);
+                if (WOBS) {                                // the previous step's bulk store must have read the buffer
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
+                const uint32_t caught = walk_row<X, WOBS>(row, orow, x, f, P.catch_tol, alive);
+                float gn[J];
+                uint32_t alive1;
+                settle_step<J, WOBS>(P, lane, env0, valid, x, rowlen, neg, alive, caught, sc.a, gn, total, alive1, eplen, rew, done,
+                                     ground_steps, blk_stat, obuf, pts);
+                alive = alive1;
+#pragma unroll
+                for (int i = 0; i < J; ++i) sc.g[i] = gn[i];
+                if (valid) {
+                    st_hint(P.reward + env, rew, pol_stream);
+                    st_hint(P.done + env, done, pol_stream);
+                }
+                if (WOBS) {
+                    if (full) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, obuf, tile_bytes, pol_stream);
+                            bulk_commit();
+                        }
+                    } else if (valid) {
+                        float *dst = P.obs + env * rowlen;
+                        for (int i = 0; i < rowlen; ++i) dst[i] = lds_f(orow + 4u * i);
+                    }
+                }
+            }
+            // the tile's state goes back to HBM once
+            if (J == 4) {
+                st_hint(reinterpret_cast<float4 *>(P.goals + env * 4), make_float4(sc.g[0], sc.g[1], sc.g[2], sc.g[3]), pol_keep);
+            } else {
+#pragma unroll
+                for (int i = 0; i < J; ++i) st_hint(P.goals + env * J + i, sc.g[i], pol_keep);
+            }
+            st_hint(P.alive + env, ep_shift ? (alive | (eplen << ep_shift)) : alive, pol_keep);
+            st_hint(P.total_reward + env, total, pol_keep);
+            if (!ep_shift) st_hint(P.counters + env, eplen, pol_keep);
+            int li = 0;
+            if (lane == 0) li = atom_add_s(queue, 1);
+            cur = tile_of(__reduce_max_sync(0xffffffffu, li));
+            fence_async_smem();                            // a reset's refresh of the row (generic proxy) vs the next bulk copy into it
+            __syncwarp();                                  // every lane is done with the objectives before the next fetch
+        }
+        if (WOBS && lane == 0) bulk_wait_read0();
+    }
+    block_epilogue(P, lane, wpb, ground_steps, blk_stat, &warps_done);
 }
 
 }  // namespace mt

@@ -352,3 +352,46 @@ def test_multi_gpu_c_host_runs(mt, tmp_path):
     res = subprocess.run([exe, str(g), "20000", "30"], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr + res.stdout
     assert f"gpus {g} x envs 20000 x steps 30: {g * 20000 * 30} env-steps" in res.stdout
+
+
+# --------------------------------------------------------------------------
+# multi-step rollout in one launch (rollout_kernel) == the same steps as separate launches
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("arm_name,n,x,obs,oar", [("ref", 150_003, 10, True, False), ("ref", 40_000, 10, False, False),
+                                                  ("ref", 5_000, 7, True, True), ("ref", 33, 32, True, False),
+                                                  ("ur5", 90_001, 20, True, True), ("ur5", 3_000, 5, False, False)])
+def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oar):
+    """mt_rollout_random(k) keeps a tile's pose / alive word / total reward in registers and its objectives in shared
+    memory for all k steps (one launch); MT_ROLLOUT_PERSISTENT=0 forces k launches of the step kernel.  Outputs of
+    the last step, state, objectives, statistics and the step index must be bit-identical -- through in-kernel
+    resets (horizon 4 < k), the first-observation-after-reset option, ragged sizes, odd / even / maximum objective
+    counts, and both built-in arms."""
+    import torch
+    arm = mt.UR5_ARM if arm_name == "ur5" else mt.REFERENCE_ARM
+    kw = dict(arm=arm, device=0, seed=13, auto_reset=True, horizon=4, obs_after_reset=oar)
+    res = []
+    for persistent in ("1", "0"):
+        os.environ["MT_ROLLOUT_PERSISTENT"] = persistent
+        try:
+            env = mt.BatchedEnvs(n, x, **kw)
+            env.reset()
+            l0 = env.launch_count
+            outs = []
+            for k in (7, 2, 11):
+                o, r, d = env.rollout_random(k, write_obs=obs)
+                outs.append((o.clone() if obs else None, r.clone(), d.clone()))
+            launches = env.launch_count - l0
+            res.append((outs, {k2: v.clone() for k2, v in env.get_state().items()}, env.get_points(False).clone(), env.stats(),
+                        env.step_index, launches))
+        finally:
+            os.environ.pop("MT_ROLLOUT_PERSISTENT", None)
+    (oa, sa, pa, ta, ia, la), (ob, sb, pb, tb, ib, lb) = res
+    assert la == 3 and lb == 20, (la, lb)                     # one launch per call against one per step
+    for (o1, r1, d1), (o2, r2, d2) in zip(oa, ob):
+        if obs:
+            assert torch.equal(o1, o2)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2)
+    for key in sa:
+        assert torch.equal(sa[key], sb[key]), key
+    assert torch.equal(pa, pb) and ta == tb and ia == ib == 20
+    assert ta["env_steps"] == 20 * n and ta["episodes"] >= 4 * n
