@@ -134,17 +134,6 @@ __device__ __forceinline__ void sincos_deg_small(float x, float &s, float &c) {
 // 2 atan(t) in degrees for two arguments in [0, 1] (the half-angle form of atan2_deg_pos)
 __device__ __forceinline__ float2 atan_half_deg2(float2 t) {
     float2 s = mul2(t, t);
-#ifdef MT_V_ATAN7
-    float2 p = bc2(-0.54776114f);
-    p = fma2(p, s, bc2(2.81390548f));
-    p = fma2(p, s, bc2(-6.86439371f));
-    p = fma2(p, s, bc2(11.3934412f));
-    p = fma2(p, s, bc2(-16.0764885f));
-    p = fma2(p, s, bc2(22.8855038f));
-    p = fma2(p, s, bc2(-38.1957664f));
-    p = fma2(p, s, bc2(114.591545f));
-    return mul2(p, t);
-#else
     float2 p = bc2(0.917460918f);
     p = fma2(p, s, bc2(-4.29046488f));
     p = fma2(p, s, bc2(9.66606236f));
@@ -153,7 +142,6 @@ __device__ __forceinline__ float2 atan_half_deg2(float2 t) {
     p = fma2(p, s, bc2(-38.1899414f));
     p = fma2(p, s, bc2(114.591492f));
     return mul2(p, t);
-#endif
 }
 
 // ------------------------------------------------------------------ Philox

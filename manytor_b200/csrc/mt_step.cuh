@@ -26,6 +26,10 @@
 
 namespace mt {
 
+#ifndef MT_SUBPOSE_UNROLL
+#define MT_SUBPOSE_UNROLL 4      // iterations (pairs of sub-poses) of the ground-test loop unrolled together
+#endif
+constexpr int kSubposeUnroll = MT_SUBPOSE_UNROLL;
 constexpr int kTile = 32;
 // Warps per block is a launch-time choice (blockDim.x / 32): as many as one SM can hold in ONE block (28
 // for the reference arm at x = 10: 72 registers, 7.7 KB of tile buffers per warp), because the warps of a
@@ -208,11 +212,7 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
             float2 sd12, cd12;
             float sd3, cd3;
             sincos_deg_small2(make_float2(d1, d2), sd12, cd12);
-#ifdef MT_V_D3PACKED
-            { float2 s33, c33; sincos_deg_small2(bc2(d3), s33, c33); sd3 = s33.x; cd3 = c33.x; }
-#else
             sincos_deg_small(d3, sd3, cd3);
-#endif
             const float sd1 = sd12.x, cd1 = cd12.x;
             // A = th1 + th3, B = th1 - th3: cos/sin of the angles and of their steps by angle addition
             const float cA = fmaf(c1, c3, -(s1 * s3)), cB = fmaf(c1, c3, s1 * s3);
@@ -225,7 +225,7 @@ __device__ __forceinline__ void ref_arm(const float *g, const float *a, int subs
             uA.init(0.5f * L2 * cA, 0.5f * L2 * sA, sdA, cdA);
             uB.init(0.5f * L2 * cB, 0.5f * L2 * sB, sdB, cdB);
             const int iters = (substeps - 1) >> 1;
-#pragma unroll 4
+#pragma unroll kSubposeUnroll
             for (int it = 0; it < iters; ++it) {
                 u1.back(); q2.back(); uA.back(); uB.back();
                 const float2 t = fma2(q2.x, add2(uA.x, neg2(uB.x)), add2(u1.x, add2(uA.x, uB.x)));
@@ -625,13 +625,15 @@ __device__ __forceinline__ void draw_actions(const StepParams &P, unsigned long 
     }
 }
 
-// Per-env pose and action of one tile, prefetched into registers one tile ahead (the kinematics need them
-// first).  The other two state words (alive | episode length, total reward) are only needed after the
-// kinematics, so they are loaded at the top of their own tile's iteration -- the ~450 instructions of
-// kinematics per warp cover the latency -- instead of living in registers for a whole tile as well.
+// Per-env scalars of one tile, prefetched into registers one tile ahead.  (Loading the two state words
+// that are only needed after the kinematics at the top of their own tile instead -- two registers fewer --
+// was measured: +1.2 us per step under back-to-back launches, the kinematics do not cover a loaded HBM.)
 template <int J>
 struct TileScalars {
     float g[J], a[J];
+    uint32_t word;    // the state word: alive mask (| ep_len << ep_shift in the packed layout)
+    float total;
+    uint32_t cnt;     // ep_len in the wide layout
 };
 
 // Where the episode length lives (StepParams::ep_shift): a compile-time objective count of at most 16 always
@@ -639,11 +641,7 @@ struct TileScalars {
 // and its selects from those kernels; otherwise the handle's choice is read at run time.
 template <int X>
 __device__ __forceinline__ int ep_shift_of(const StepParams &P) {
-#ifdef MT_V_EPRUNTIME
-    return P.ep_shift;
-#else
     return (X > 0 && X <= 16) ? 16 : P.ep_shift;
-#endif
 }
 
 template <int J, int X, bool RAND>
@@ -689,6 +687,9 @@ __device__ __forceinline__ void load_scalars(const StepParams &P, int env32, Til
             for (int i = 0; i < J; ++i) s.a[i] = ld_hint(P.actions + env * J + i, stream);
         }
     }
+    s.word = ld_hint(P.alive + env, keep);
+    s.total = ld_hint(P.total_reward + env, keep);
+    s.cnt = ep_shift_of<X>(P) ? 0u : ld_hint(P.counters + env, keep);
 }
 
 // ---------------------------------------------------------------------------
@@ -930,10 +931,10 @@ step_kernel(const __grid_constant__ StepParams P) {
             const bool full = env0 + kTile <= n_envs;  // warp-uniform
             const bool valid = env32 < n_envs;
 
-            // 1. this tile's state words and the next tile's pose / action on their way to registers
-            const uint32_t word = ld_hint(P.alive + env, pol_keep);          // alive mask (| ep_len << ep_shift when packed)
-            float total = ld_hint(P.total_reward + env, pol_keep);
-            uint32_t eplen = ep_shift ? 0u : ld_hint(P.counters + env, pol_keep);
+            // 1. next tile's scalars on their way to registers
+            const uint32_t word = sc.word;
+            float total = sc.total;
+            uint32_t eplen = sc.cnt;
             TileScalars<J> sn;
             if (nxt >= 0) load_scalars<J, X, RAND>(P, nxt * kTile + lane, sn, pol_keep, pol_stream);
 
@@ -1103,10 +1104,8 @@ rollout_kernel(const __grid_constant__ StepParams P) {
             }
             TileScalars<J> sc;
             load_scalars<J, X, true>(P, env32, sc, pol_keep, pol_stream);
-            uint32_t alive = ld_hint(P.alive + env, pol_keep);
-            float total = ld_hint(P.total_reward + env, pol_keep);
-            uint32_t eplen = ep_shift ? 0u : ld_hint(P.counters + env, pol_keep);
-            if (ep_shift) { eplen = alive >> ep_shift; alive &= amask; }
+            uint32_t alive = sc.word & amask, eplen = ep_shift ? sc.word >> ep_shift : sc.cnt;
+            float total = sc.total;
             float rew = 0.f;
             uint8_t done = 0;
             for (int s = 0; s < P.n_steps; ++s) {

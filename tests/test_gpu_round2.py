@@ -372,6 +372,7 @@ def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oa
     res = []
     for persistent in ("1", "0"):
         os.environ["MT_ROLLOUT_PERSISTENT"] = persistent
+        os.environ["MT_DISABLE_JIT"] = "1"     # other objective counts would get NVRTC-specialised step kernels (no rollout kernel)
         try:
             env = mt.BatchedEnvs(n, x, **kw)
             env.reset()
@@ -385,6 +386,7 @@ def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oa
                         env.step_index, launches))
         finally:
             os.environ.pop("MT_ROLLOUT_PERSISTENT", None)
+            os.environ.pop("MT_DISABLE_JIT", None)
     (oa, sa, pa, ta, ia, la), (ob, sb, pb, tb, ib, lb) = res
     assert la == 3 and lb == 20, (la, lb)                     # one launch per call against one per step
     for (o1, r1, d1), (o2, r2, d2) in zip(oa, ob):
