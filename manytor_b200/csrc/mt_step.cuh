@@ -785,9 +785,29 @@ __device__ __forceinline__ void settle_step(const StepParams &P, int lane, int e
     __syncwarp();
 }
 
-// Warp -> block -> device bookkeeping at the end of a launch: every warp adds its ground-contact count to the
-// block's shared-memory accumulators; the block's last warp flushes them with one atomic per non-zero word;
-// the launch's last block (ticket) adds the launch's env-steps and advances the step index by `P.advance`.
+// Device-side bookkeeping of a launch, kept OFF the tail of the launch (a returning atomic or a fence at the
+// end of every block lengthens the launch by its round trip, and the next step cannot start before the whole
+// grid has completed: measured +2 us per step when the ticket sat in the epilogue).
+//
+// launch_ticket, at the START of a block: every warp calls it once it has read the step index (`seen` carries a
+// data dependence on that load); the block's last warp takes the launch's ticket, and the launch's last block --
+// at which point every block has read the old step index -- advances it by P.advance and adds the launch's
+// env-steps.  The round trip overlaps the warp's first tile fetch.
+__device__ __forceinline__ void launch_ticket(const StepParams &P, int lane, int wpb, unsigned long long seen,
+                                              unsigned int *warps_seen) {
+    if (lane != 0) return;
+    if (atomicAdd(warps_seen, 1u + (unsigned)(seen >> 63)) != (unsigned)wpb - 1u) return;
+    __threadfence();
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(P.ctrl + kCtrlTicket + P.ticket_slot);
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
+        atomicExch(ticket, 0u);
+        atomicAdd(P.stats, (unsigned long long)P.launch_envs);
+        if (P.advance) atomicAdd(P.ctrl + kCtrlStep, (unsigned long long)P.advance);
+    }
+}
+
+// block_epilogue, at the END: every warp adds its ground-contact count to the block's shared-memory accumulators;
+// the block's last warp flushes them with one fire-and-forget atomic per non-zero word.
 __device__ __forceinline__ void block_epilogue(const StepParams &P, int lane, int wpb, uint32_t ground_steps,
                                                unsigned long long *blk_stat, unsigned int *warps_done) {
     if (lane != 0) return;
@@ -799,13 +819,6 @@ __device__ __forceinline__ void block_epilogue(const StepParams &P, int lane, in
     for (int k = 0; k < kBlockStats; ++k) {
         const unsigned long long v = reinterpret_cast<volatile unsigned long long *>(blk_stat)[k];
         if (v) atomicAdd(P.stats + 1 + k, v);
-    }
-    __threadfence();
-    unsigned int *ticket = reinterpret_cast<unsigned int *>(P.ctrl + kCtrlTicket + P.ticket_slot);
-    if (atomicAdd(ticket, 1u) == gridDim.x - 1u) {
-        atomicExch(ticket, 0u);
-        atomicAdd(P.stats, (unsigned long long)P.launch_envs);
-        if (P.advance) atomicAdd(P.ctrl + kCtrlStep, (unsigned long long)P.advance);
     }
 }
 
@@ -840,7 +853,7 @@ __global__ void __launch_bounds__(((ARM == 0) ? kMaxWarpsRefArm : kMaxWarpsGener
 step_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int queue_next;
-    __shared__ unsigned int warps_done;
+    __shared__ unsigned int warps_done, warps_seen;
     __shared__ unsigned long long blk_stat[kBlockStats];
     constexpr int J = ArmJoints<ARM>::value;
     // Everything that is the same for the whole warp is made PROVABLY warp-uniform (a warp reduction's result
@@ -895,6 +908,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     if (threadIdx.x == 0) {
         queue_next = wpb;                   // the first wpb tiles of the block go to its warps directly
         warps_done = 0u;
+        warps_seen = 0u;
 #pragma unroll
         for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
     }
@@ -912,15 +926,17 @@ step_kernel(const __grid_constant__ StepParams P) {
     }
     griddep_wait();                         // ... but nothing touches the state before the previous step is complete
     uint32_t ground_steps = 0;              // warp-uniform: ground-contact env-steps of this warp's tiles
-    if (cur >= 0) {                         // (a warp without a tile still takes part in the block's epilogue)
-        // the step index keys the in-kernel action stream; it lives in device memory and was advanced by the
-        // previous launch's last block (visible here: griddepcontrol.wait orders after that grid's completion)
-        unsigned long long step_index = 0ull;
-        if (RAND) step_index = ld_volatile_u64(P.ctrl + kCtrlStep);
+    // the step index keys the in-kernel action stream; it lives in device memory and was advanced by the
+    // previous launch (visible here: griddepcontrol.wait orders after that grid's completion)
+    unsigned long long step_index = 0ull;
+    if (RAND && cur >= 0) step_index = ld_volatile_u64(P.ctrl + kCtrlStep);
+    if (cur < 0) launch_ticket(P, lane, wpb, step_index, &warps_seen);
+    if (cur >= 0) {                         // (a warp without a tile still takes part in the block's bookkeeping)
         if (lane == 0) fetch_points(cur, buf0, bar0);
         __syncwarp();
         TileScalars<J> sc;
         load_scalars<J, X, RAND>(P, cur * kTile + lane, sc, pol_keep, pol_stream);
+        launch_ticket(P, lane, wpb, step_index, &warps_seen);   // its round trip overlaps the tile's fetch
         int nxt = grab_tile();
         const int ep_shift = ep_shift_of<X>(P);
         const uint32_t amask = ep_shift ? ((1u << ep_shift) - 1u) : 0xffffffffu;
@@ -1055,7 +1071,7 @@ __global__ void __launch_bounds__(((ARM == 0) ? kMaxWarpsRefArm : kMaxWarpsGener
 rollout_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int queue_next;
-    __shared__ unsigned int warps_done;
+    __shared__ unsigned int warps_done, warps_seen;
     __shared__ unsigned long long blk_stat[kBlockStats];
     constexpr int J = ArmJoints<ARM>::value;
     constexpr int NB = WOBS ? 2 : 1;                      // objectives (+ observations) of the warp's tile
@@ -1077,6 +1093,7 @@ rollout_kernel(const __grid_constant__ StepParams P) {
     if (threadIdx.x == 0) {
         queue_next = wpb;
         warps_done = 0u;
+        warps_seen = 0u;
 #pragma unroll
         for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
     }
@@ -1089,8 +1106,9 @@ rollout_kernel(const __grid_constant__ StepParams P) {
     }
     griddep_wait();
     uint32_t ground_steps = 0;
+    const unsigned long long step0 = cur >= 0 ? ld_volatile_u64(P.ctrl + kCtrlStep) : 0ull;
+    launch_ticket(P, lane, wpb, step0, &warps_seen);
     if (cur >= 0) {
-        const unsigned long long step0 = ld_volatile_u64(P.ctrl + kCtrlStep);
         const int ep_shift = ep_shift_of<X>(P);
         const uint32_t amask = ep_shift ? ((1u << ep_shift) - 1u) : 0xffffffffu;
         const uint32_t row = pts + (uint32_t)(lane * rowlen) * 4u, orow = obuf + (uint32_t)(lane * rowlen) * 4u;

@@ -503,9 +503,10 @@ class Environment:
         """manytor.py:255-260 -> (obs2 (3X,) float64, reward int, done bool)."""
         act = np.asarray(action, dtype=np.float32).reshape(1, self._envs.j)
         before = self._envs.fetch_env(0) if self._renderer is not None else None
-        obs, rew, done = self._envs.step(act)
-        obs = obs.cpu().numpy().astype(np.float64)[0]
-        d = int(done.cpu().numpy()[0])
+        # host-buffer step: upload, kernel and read-back in ONE synchronous call (a batch of one is pure latency)
+        obs, rew, done = self._envs.step_host(act)
+        obs = obs.astype(np.float64)[0]
+        d = int(done[0])
         self._traj.append(self._pose, act[0])                                  # manytor.py:190, materialised on read
         self._pose = act[0].astype(np.float64)
         if d and self._envs.cfg.auto_reset:                                    # the kernel has already reset this env
@@ -513,7 +514,7 @@ class Environment:
             self._pose = np.zeros(self._envs.j)
         if before is not None:
             self._renderer.frames(self.id, before["goals"], act[0], before["points"])
-        return obs, int(rew.cpu().numpy()[0]), bool(d) if self._horizon > 0 else bool(d & 1)
+        return obs, int(rew[0]), bool(d) if self._horizon > 0 else bool(d & 1)
 
     def render(self, stop_render=False, multienv=False):
         """manytor.py:262-283."""
