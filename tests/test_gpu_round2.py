@@ -397,3 +397,16 @@ def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oa
         assert torch.equal(sa[key], sb[key]), key
     assert torch.equal(pa, pb) and ta == tb and ia == ib == 20
     assert ta["env_steps"] == 20 * n and ta["episodes"] >= 4 * n
+
+
+def test_policy_loop_example_feeds_fresh_observations(mt):
+    """examples/policy_loop.py (the zero-copy hand-off pattern INTEGRATION.md points to): reset() and step() must
+    return the SAME observation storage, so that a policy -- eager or captured in a CUDA graph -- keeps reading
+    fresh observations (it used to read the reset observations forever).  The example asserts it."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "examples", "policy_loop.py"), "8192", "30"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:] + res.stdout[-500:]
+    assert "graph :" in res.stdout and "episode statistics" in res.stdout
