@@ -68,7 +68,9 @@ struct mt_env {
     bool jit = false;
     int jit_id = 0, jit_x = 0;
     std::string jit_preset;
-    cudaKernel_t jit_kernel[2][2] = {};
+    cudaKernel_t jit_kernel[2][2] = {};      // [in-kernel actions][observations written]
+    cudaKernel_t jit_rollout[2] = {};        // multi-step rollout kernel, [observations written]
+    bool jit_rollout_failed = false;
     float *goals = nullptr, *total_reward = nullptr, *points = nullptr;
     uint32_t *alive = nullptr, *counters = nullptr, *episode = nullptr;
     unsigned long long *stats = nullptr;   // MT_STATS_WORDS: env_steps, finished-episode sums, ground steps (device side)
@@ -792,8 +794,8 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     return MT_OK;
 }
 
-// Multi-step random rollout in ONE launch (rollout_kernel, mt_step.cuh): built-in arms only; handles whose step
-// kernels come from NVRTC, and run-time DH tables, take the per-step launches instead (returns false).
+// Multi-step random rollout in ONE launch (rollout_kernel, mt_step.cuh): built-in arms and handles whose kernels
+// come from NVRTC; run-time DH tables take the per-step launches instead (`launched` stays false).
 template <int ARM>
 static StepFn pick_rollout_x(int x, bool wobs) {
     switch (x) {
@@ -815,10 +817,25 @@ static StepFn pick_rollout(int arm, int x, bool wobs) {
 
 static int launch_rollout(mt_env *e, int n_steps, float *obs, float *reward, uint8_t *done, cudaStream_t st, bool &launched) {
     launched = false;
-    if (e->jit || n_steps < 2) return MT_OK;
+    if (n_steps < 2) return MT_OK;
     if (const char *v = std::getenv("MT_ROLLOUT_PERSISTENT"))
         if (v[0] == '0') return MT_OK;
-    const void *fn = (const void *)pick_rollout(e->arm, e->cfg.n_obj, obs != nullptr);
+    const void *fn = nullptr;
+    if (e->jit) {                                             // this handle's own table: compiled on first use
+        if (e->jit_rollout_failed) return MT_OK;
+        cudaKernel_t &k = e->jit_rollout[obs ? 1 : 0];
+        if (!k) {
+            std::string err;
+            k = jit_step_kernel(e->jit_preset, e->jit_id, e->jit_x, true, obs != nullptr, err, true).kernel;
+            if (!k) {
+                e->jit_rollout_failed = true;                 // keep working through the per-step launches
+                return MT_OK;
+            }
+        }
+        fn = (const void *)k;
+    } else {
+        fn = (const void *)pick_rollout(e->arm, e->cfg.n_obj, obs != nullptr);
+    }
     if (!fn) return MT_OK;
     StepParams P = e->base;
     P.actions = nullptr;

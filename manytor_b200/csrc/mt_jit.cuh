@@ -93,11 +93,16 @@ static std::string preset_source(int id, int J, const JointConst *rows) {
 
 // Compile (or fetch from the per-process cache) step_kernel<id, x_template, rnd, wobs> for the table
 // described by `preset`.  Returns an empty JitKernel and fills `err` on failure.
-static JitKernel jit_step_kernel(const std::string &preset, int id, int x_template, bool rnd, bool wobs, std::string &err) {
+// `rollout` selects the multi-step rollout_kernel<id, x_template, wobs> (in-kernel actions; `rnd` is ignored).
+static JitKernel jit_step_kernel(const std::string &preset, int id, int x_template, bool rnd, bool wobs, std::string &err,
+                                 bool rollout = false) {
     static std::mutex mu;
     static std::map<std::string, JitKernel> cache;
-    const std::string inst = "mt::step_kernel<" + std::to_string(id) + ", " + std::to_string(x_template) + ", " +
-                             (rnd ? "true" : "false") + ", " + (wobs ? "true" : "false") + ">";
+    const std::string targs = rollout ? std::to_string(id) + ", " + std::to_string(x_template) + ", " + (wobs ? "true" : "false")
+                                      : std::to_string(id) + ", " + std::to_string(x_template) + ", " + (rnd ? "true" : "false") +
+                                            ", " + (wobs ? "true" : "false");
+    const std::string kname = rollout ? "rollout_kernel" : "step_kernel";
+    const std::string inst = "mt::" + kname + "<" + targs + ">";
     const std::string key = preset + inst;
     std::lock_guard<std::mutex> lock(mu);
     auto hit = cache.find(key);
@@ -108,9 +113,8 @@ static JitKernel jit_step_kernel(const std::string &preset, int id, int x_templa
         err = "libnvrtc not found";
         return out;
     }
-    const std::string src = "#include \"mt_step.cuh\"\nnamespace mt {\n" + preset + "template __global__ void step_kernel<" +
-                            std::to_string(id) + ", " + std::to_string(x_template) + ", " + (rnd ? "true" : "false") + ", " +
-                            (wobs ? "true" : "false") + ">(const __grid_constant__ StepParams);\n}\n";
+    const std::string src = "#include \"mt_step.cuh\"\nnamespace mt {\n" + preset + "template __global__ void " + kname + "<" +
+                            targs + ">(const __grid_constant__ StepParams);\n}\n";
     std::vector<const char *> names(kEmbeddedHeaderNames, kEmbeddedHeaderNames + kEmbeddedHeaderCount);
     std::vector<const char *> sources(kEmbeddedHeaderSources, kEmbeddedHeaderSources + kEmbeddedHeaderCount);
     for (int i = 0; i < 3; ++i) {

@@ -359,7 +359,8 @@ def test_multi_gpu_c_host_runs(mt, tmp_path):
 # --------------------------------------------------------------------------
 @pytest.mark.parametrize("arm_name,n,x,obs,oar", [("ref", 150_003, 10, True, False), ("ref", 40_000, 10, False, False),
                                                   ("ref", 5_000, 7, True, True), ("ref", 33, 32, True, False),
-                                                  ("ur5", 90_001, 20, True, True), ("ur5", 3_000, 5, False, False)])
+                                                  ("ur5", 90_001, 20, True, True), ("ur5", 3_000, 5, False, False),
+                                                  ("ref-jit", 9_000, 7, True, False), ("custom-jit", 70_000, 12, True, True)])
 def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oar):
     """mt_rollout_random(k) keeps a tile's pose / alive word / total reward in registers and its objectives in shared
     memory for all k steps (one launch); MT_ROLLOUT_PERSISTENT=0 forces k launches of the step kernel.  Outputs of
@@ -367,12 +368,17 @@ def test_multi_step_rollout_equals_per_step_launches(mt, arm_name, n, x, obs, oa
     resets (horizon 4 < k), the first-observation-after-reset option, ragged sizes, odd / even / maximum objective
     counts, and both built-in arms."""
     import torch
-    arm = mt.UR5_ARM if arm_name == "ur5" else mt.REFERENCE_ARM
+    jit = arm_name.endswith("jit")            # NVRTC-specialised kernels (another objective count / a user's DH table)
+    custom = mt.ArmSpec(dh=((0.0, np.pi / 2, 0.30, 0.0), (0.50, 0.0, 0.0, 0.2), (0.40, 0.3, 0.10, 0.0),
+                            (0.0, -np.pi / 2, 0.20, -np.pi / 2), (0.10, 0.0, 0.05, 0.0)),
+                        obs_frame=4, ground_frames=(4, 5), catch_frame=5, radius=0.9, catch_tol=0.15)
+    arm = mt.UR5_ARM if arm_name == "ur5" else (custom if arm_name == "custom-jit" else mt.REFERENCE_ARM)
     kw = dict(arm=arm, device=0, seed=13, auto_reset=True, horizon=4, obs_after_reset=oar)
     res = []
     for persistent in ("1", "0"):
         os.environ["MT_ROLLOUT_PERSISTENT"] = persistent
-        os.environ["MT_DISABLE_JIT"] = "1"     # other objective counts would get NVRTC-specialised step kernels (no rollout kernel)
+        if not jit:
+            os.environ["MT_DISABLE_JIT"] = "1"     # built-in kernels with a run-time objective count
         try:
             env = mt.BatchedEnvs(n, x, **kw)
             env.reset()
