@@ -512,12 +512,13 @@ def run_gpu(args) -> None:
                         "best_ms_per_step": best_total / K, "best_value": world * n * K / (best_total * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, committed in profiles/traffic.json (a constant of the kernel, NOT measured in this run)",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch in steady state (mean of 20 consecutive warm launches under ncu --cache-control none), committed in profiles/traffic.json with the cold isolated-launch figure beside it (a constant of the kernel, NOT measured in this run)",
                          "peak_source": peak_src, "kernel": "mt::step_kernel<0,10,false,true>",
                          "algorithmic_bytes_per_env_step": B, "kernel_ms_per_launch": kernel_ms,
                          "envs_per_launch": n,
                          # the algorithmic count includes the 48 B/env-step of per-env state that the kernel keeps in
-                         # L2 from launch to launch, so `frac` can pass 1; this is the DRAM side on its own
+                         # L2 from launch to launch, so `frac` can pass 1; this is the DRAM side on its own: the
+                         # steady-state traffic (streamed arrays only, no re-reads) over this run's kernel time
                          "dram_achieved": (traffic / kernel_ms / 1e6) if traffic else None,
                          "dram_frac": (traffic / kernel_ms / 1e6 / peak) if traffic else None},
             "cpu_baseline": cpu,
