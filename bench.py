@@ -460,8 +460,8 @@ def run_gpu(args) -> None:
         a = env.pinned(f"actions{i}", (n, 4), np.float32)
         a[:] = rs.randint(-180, 180, size=(n, 4))
         e2e_acts.append(a)
-    for i in range(2):
-        env.step_host(e2e_acts[i])
+    for i in range(5):                                      # untimed: the handle times both host-step variants on its first 4 calls
+        env.step_host(e2e_acts[i % e2e_steps])
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
@@ -523,7 +523,8 @@ def run_gpu(args) -> None:
                          "dram_frac": (traffic / kernel_ms / 1e6 / peak) if traffic else None},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers, 16 chunks over 4 streams)",
+                    "steps": e2e_steps, "api": "BatchedEnvs.step_host -> mt_step_host (pinned host buffers; staged = 16 chunks over 4 streams, zero-copy = one launch on the host buffers; the handle keeps whichever its first calls timed faster)",
+                    "host_step_mode": env.host_step_mode,
                     "cpu_binding": f"{len(cores)} cores next to the GPU (NVML affinity)" if cores else "none",
                     "d2h_only_ceiling": ceiling, "frac_of_d2h_ceiling": e2e_value / ceiling,
                     "ceiling_note": f"bare pinned D2H of the same {d2h} B per step on all {world} ranks at once: "

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mt_sample_actions": (C.c_int, [_P, _P, _P]),
     "mt_rollout_random": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "mt_step_host": (C.c_int, [_P, _P, _P, _P, _P]),
+    "mt_host_step_mode": (C.c_int, [_P]),
     "mt_host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
     "mt_host_free": (C.c_int, [_P]),
     "mt_set_points": (C.c_int, [_P, _P, _P, _P]),

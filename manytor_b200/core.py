@@ -271,6 +271,11 @@ class BatchedEnvs:
                                           rew.ctypes.data, done.ctypes.data))
         return obs, rew, done
 
+    @property
+    def host_step_mode(self) -> str:
+        """Which implementation `step_host` settled on for this handle (it times both on its first calls)."""
+        return {0: "staged", 1: "zero-copy", 2: "deciding"}.get(int(self._lib.mt_host_step_mode(self._h)), "?")
+
     # -- state exchange ---------------------------------------------------------
     def set_points(self, points, mask=None):
         p = self._as_dev(points, torch.float32, (self.n, self.x, 3))

@@ -3,6 +3,7 @@
 // path here: without a CUDA device every entry point fails with MT_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -95,7 +96,9 @@ struct mt_env {
     static constexpr int kStreams = 4;
     cudaStream_t hs[kStreams] = {};
     cudaEvent_t hev[kStreams + 1] = {};       // per stream "kernels done"; [kStreams] = entry fence
-    bool zero_copy = false;
+    // mt_step_host variant: 0 staged, 1 zero-copy, 2 auto (decided from the first calls' own timings)
+    int host_mode = 2, host_calls = 0;
+    double host_best[2] = {1e30, 1e30};
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t *h_done = nullptr;
     // timing
@@ -982,13 +985,28 @@ extern "C" int mt_host_free(void *p) {
     return MT_OK;
 }
 
-// Host-buffer step.  Default: chunks of whole tiles round-robin over internal streams, each chunk
-// H2D(actions) -> step kernel -> D2H(observations), then reward/done in two copies at the end; the
-// copies of one chunk overlap the kernels and copies of the others, and the whole call is bound by the
-// PCIe read-back of the observations (120 of the 125 B per env).  The internal streams are ordered after
-// everything submitted earlier to blocking streams (an event on the legacy default stream), not by a
-// device-wide synchronisation.  MT_HOST_ZEROCOPY=1 selects the variant that hands the pinned host
-// buffers to ONE step launch directly (actions read and results written across PCIe by the kernel).
+// Host-buffer step, two variants.
+//   staged     chunks of whole tiles round-robin over internal streams, each chunk H2D(actions) -> step kernel ->
+//              D2H(observations), then reward/done in two copies at the end; the copies of one chunk overlap the
+//              kernels and copies of the others.
+//   zero-copy  ONE step launch on the pinned host buffers themselves: the kernel reads the actions and bulk-stores
+//              the observations across PCIe, no staging copy, no chunking.
+// Either way the call is bound by the PCIe read-back of the observations (120 of the 125 B per env).  Which one is
+// faster depends on the box: alone on a link staging wins (93 % vs 87 % of the link), with 8 GPUs sharing the host's
+// 93 GB/s zero-copy does (99 % vs 94 %).  So by default the handle TIMES both on its first calls (the call is
+// synchronous, results are identical) and keeps the faster; MT_HOST_ZEROCOPY=0/1 pins the choice.  The internal
+// streams are ordered after everything submitted earlier to blocking streams (an event on the legacy default stream),
+// not by a device-wide synchronisation.
+static bool device_visible_host(const void *p) {
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p && ((uintptr_t)p & 15u) == 0;
+}
+
 extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_host, float *reward_host,
                             uint8_t *done_host) {
     if (!e) return fail(MT_ERR_INVALID, "env is NULL");
@@ -999,18 +1017,32 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
     if (!e->hs[0]) {
         for (auto &s : e->hs) CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         for (auto &v : e->hev) CU(cudaEventCreateWithFlags(&v, cudaEventDisableTiming));
-        const char *zc = std::getenv("MT_HOST_ZEROCOPY");
-        e->zero_copy = zc && zc[0] == '1';
+        if (const char *zc = std::getenv("MT_HOST_ZEROCOPY"))
+            if (zc[0] == '0' || zc[0] == '1') e->host_mode = zc[0] - '0';
     }
+    // calls 0-1 staged, 2-3 zero-copy (the first of each pair untimed: allocations, first-touch), then the faster one
+    const int call = e->host_calls;
+    bool zero_copy = e->host_mode == 1 || (e->host_mode == 2 && (call == 2 || call == 3));
+    if (zero_copy && !(device_visible_host(actions_host) && device_visible_host(obs_host) && device_visible_host(reward_host) &&
+                       device_visible_host(done_host))) {
+        if (e->host_mode == 1) return fail(MT_ERR_INVALID, "MT_HOST_ZEROCOPY=1 needs buffers from mt_host_alloc (pinned, mapped, 16-byte aligned)");
+        e->host_mode = 0;                                     // pageable or unaligned buffers: staging only
+        zero_copy = false;
+    }
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto finish = [&]() {
+        if (e->host_mode != 2) return;
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        if (call == 1 || call == 3) e->host_best[zero_copy ? 1 : 0] = dt;
+        if (++e->host_calls == 4) e->host_mode = e->host_best[1] < 0.98 * e->host_best[0] ? 1 : 0;
+    };
     CU(cudaEventRecord(e->hev[mt_env::kStreams], nullptr));       // everything submitted so far (blocking streams)
-    if (e->zero_copy) {
-        int rc;
-        if ((rc = check_ptr(actions_host, "actions_host", true))) return rc;
-        if ((rc = check_ptr(obs_host, "obs_host", false))) return rc;
+    if (zero_copy) {
         CU(cudaStreamWaitEvent(e->hs[0], e->hev[mt_env::kStreams], 0));
-        if ((rc = launch_step(e, actions_host, obs_host, reward_host, done_host, nullptr, false, 0, e->n_tiles, e->hs[0])))
+        if (int rc = launch_step(e, actions_host, obs_host, reward_host, done_host, nullptr, false, 0, e->n_tiles, e->hs[0]))
             return rc;
         CU(cudaStreamSynchronize(e->hs[0]));
+        finish();
         return MT_OK;
     }
     if (!e->h_actions) {
@@ -1042,8 +1074,12 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
     CU(cudaMemcpyAsync(reward_host, e->h_reward, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->hs[0]));
     CU(cudaMemcpyAsync(done_host, e->h_done, (size_t)e->n, cudaMemcpyDeviceToHost, e->hs[0]));
     CU(cudaStreamSynchronize(e->hs[0]));
+    finish();
     return MT_OK;
 }
+
+// which variant mt_step_host uses: 0 staged, 1 zero-copy, 2 still deciding (see above)
+extern "C" int mt_host_step_mode(const mt_env *e) { return e ? e->host_mode : -1; }
 
 extern "C" int mt_set_points(mt_env *e, const float *points_dev, const uint8_t *mask_dev, void *stream) {
     if (!e || !points_dev) return fail(MT_ERR_INVALID, "NULL argument");
