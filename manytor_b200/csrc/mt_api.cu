@@ -1177,7 +1177,9 @@ extern "C" int mt_stats_device(mt_env *e, int64_t *stats_dev, void *stream) {
     DeviceGuard guard(e->cfg.device);
     cudaStream_t st = (cudaStream_t)stream;
     CU(cudaMemsetAsync(stats_dev, 0, MT_STATS_WORDS * 8, st));
-    stats_kernel<<<e->num_sms, 256, 0, st>>>(e->base, (long long *)stats_dev);
+    // enough threads in flight to read the (L2-resident) total_reward array at full rate: this kernel sits inside
+    // the timed region of a rollout, right before the one collective
+    stats_kernel<<<e->num_sms * 4, 512, 0, st>>>(e->base, (long long *)stats_dev);
     CU(cudaGetLastError());
     e->launches++;
     return MT_OK;
