@@ -165,6 +165,14 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
     return v;
 }
 
+// L2 prefetches (hints: safe on data another grid may still rewrite, the L2 is the point of coherence)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *gmem) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------
 // Consecutive step launches are data dependent (step t+1 reads the state step t wrote), but the
 // next launch's block scheduling, shared-memory carve-up and barrier setup are not.  With the

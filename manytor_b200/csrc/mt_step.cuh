@@ -924,6 +924,15 @@ step_kernel(const __grid_constant__ StepParams P) {
         if (NB == 2) mbar_init_s(bar0 + 8u, 1);
         mbar_init_fence();
     }
+#ifndef MT_NO_START_PREFETCH
+    // While this block waits for the previous step's grid to drain, pull its warps' FIRST tiles towards the L2
+    // (objectives by one bulk prefetch, actions by line): the first tile of a warp is the only one whose fetch has
+    // nothing to hide behind.  Hints only -- nothing is consumed before the wait below.
+    if (cur >= 0) {
+        if (lane == 0) bulk_prefetch_l2(P.points + (size_t)cur * (size_t)(kTile * rowlen), tile_bytes);
+        if (!RAND && cur * kTile + lane < n_envs) prefetch_l2(P.actions + (size_t)(cur * kTile + lane) * J);
+    }
+#endif
     griddep_wait();                         // ... but nothing touches the state before the previous step is complete
     uint32_t ground_steps = 0;              // warp-uniform: ground-contact env-steps of this warp's tiles
     // the step index keys the in-kernel action stream; it lives in device memory and was advanced by the
