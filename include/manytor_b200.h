@@ -149,11 +149,17 @@ int mt_step(mt_env *env, const float *actions_dev, float *obs_dev, float *reward
  * (seed, global env id, step index). */
 int mt_sample_actions(mt_env *env, float *actions_dev, void *stream);
 
-/* n_steps x step(action_sample()) with the actions drawn inside the step kernel
- * (same stream of actions as mt_sample_actions).  obs_dev/reward_dev/done_dev are
- * overwritten every step; obs_dev may be NULL to skip the observation write;
- * reward_dev / done_dev may be NULL, the results then go to buffers the handle owns
- * (a host without CUDA headers can drive a rollout and read only the statistics). */
+/* n_steps x step(action_sample()) with the actions drawn inside the kernel (same stream
+ * of actions as mt_sample_actions).  obs_dev/reward_dev/done_dev are overwritten every
+ * step; obs_dev may be NULL to skip the observation write; reward_dev / done_dev may be
+ * NULL, the results then go to buffers the handle owns (a host without CUDA headers can
+ * drive a rollout and read only the statistics).
+ * For n_steps >= 2 this is ONE launch per 4096 steps of the multi-step rollout kernel:
+ * every tile of 32 envs keeps its pose / alive word / total reward in registers and its
+ * objectives in shared memory for all the steps, and only what a step produces
+ * (observations, reward, done) leaves the SM each step.  Results are bit-identical to
+ * n_steps launches of the step kernel, which run-time DH tables without NVRTC still
+ * take (MT_ROLLOUT_PERSISTENT=0 forces them for everyone). */
 int mt_rollout_random(mt_env *env, int32_t n_steps, float *obs_dev, float *reward_dev,
                       uint8_t *done_dev, void *stream);
 
