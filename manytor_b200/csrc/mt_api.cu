@@ -171,14 +171,25 @@ extern "C" int mt_config_init(mt_config *cfg) {
     return MT_OK;
 }
 
-// the two L2 eviction policies of a handle (StepParams::pol_state / pol_stream)
-__global__ void policy_kernel(unsigned long long *out, float keep_fraction) {
+// the L2 eviction policies of a handle (StepParams::pol_state / pol_stream / pol_store); kind: 0 evict_first (the
+// default for everything streamed), 1 evict_normal, 2 evict_last (MT_POL_LOAD / MT_POL_STORE = first|normal|last, tuning)
+__device__ unsigned long long policy_of(int kind) {
+    return kind == 1 ? policy_evict_normal() : (kind == 2 ? policy_evict_last() : policy_evict_first());
+}
+__global__ void policy_kernel(unsigned long long *out, float keep_fraction, int load_kind, int store_kind) {
 #ifdef MT_NO_L2_HINTS
-    out[0] = out[1] = policy_evict_last();      // A/B builds: evict_normal everywhere
+    out[0] = out[1] = out[2] = policy_evict_last();      // A/B builds: evict_normal everywhere
 #else
     out[0] = keep_fraction > 0.f ? policy_evict_last_fraction(fminf(keep_fraction, 1.0f)) : policy_evict_normal();
-    out[1] = policy_evict_first();
+    out[1] = policy_of(load_kind);
+    out[2] = policy_of(store_kind);
 #endif
+}
+
+static int policy_kind(const char *name, int fallback) {
+    const char *v = std::getenv(name);
+    if (!v) return fallback;
+    return v[0] == 'n' ? 1 : (v[0] == 'l' ? 2 : 0);
 }
 
 static int validate(const mt_config &c) {
@@ -338,8 +349,14 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
         if (const char *kb = std::getenv("MT_L2_KEEP_MB")) keep_mb = std::atof(kb);
         const double state_bytes = (4.0 * J + 8.0 + (e->ep_shift ? 0.0 : 4.0)) * (double)np;
         e->keep_fraction = (float)(keep_mb * 1048576.0 >= state_bytes ? 1.0 : keep_mb * 1048576.0 / state_bytes);
-        policy_kernel<<<1, 1>>>(e->stats, e->keep_fraction);    // the stats words are zeroed again right below
-        unsigned long long pol[2] = {0, 0};
+        // Streamed arrays (objectives, actions in; observations, reward, done out): evict_normal while the whole state fits
+        // its evict_last budget -- measured 44.0 vs 47.1 us per step at 2^20 envs, 98.1 vs 100.3 for the UR5 config
+        // (profiles/r2_ab_l2_policies.txt) -- and evict_first once it does not (2^22 envs: 231.5 vs 237.6 us), where the
+        // streams would otherwise push the protected part of the state out.
+        const int stream_kind = e->keep_fraction >= 1.0f ? 1 : 0;
+        policy_kernel<<<1, 1>>>(e->stats, e->keep_fraction, policy_kind("MT_POL_LOAD", stream_kind),
+                                policy_kind("MT_POL_STORE", stream_kind));   // the stats words are zeroed again right below
+        unsigned long long pol[3] = {0, 0, 0};
         cudaError_t pe = cudaMemcpy(pol, e->stats, sizeof(pol), cudaMemcpyDeviceToHost);
         if (pe == cudaSuccess) pe = cudaMemset(e->stats, 0, sizeof(pol));
         if (pe != cudaSuccess) {
@@ -349,6 +366,7 @@ extern "C" int mt_create(const mt_config *cfg, mt_env **out) {
         }
         e->base.pol_state = pol[0];
         e->base.pol_stream = pol[1];
+        e->base.pol_store = pol[2];
     }
     // Run-time specialisation (mt_jit.cuh): a run-time table with the usual frame selectors gets its own
     // Preset<>; a built-in arm with an objective count other than the pre-compiled 10 / 20 gets the same arm

@@ -71,9 +71,9 @@ __device__ __forceinline__ int atom_add_s(uint32_t a, int v) {
 // ---- L2 eviction policies -------------------------------------------------------------
 // The per-env state (goals, alive, total_reward, counters: 28 B/env) is read AND rewritten by
 // every step, while objectives, actions and outputs stream through once per step.  Marking the
-// state evict_last and the streams evict_first lets the 126 MB L2 keep the state resident from one
-// launch to the next (tools/microbench/l2hint.cu: -6% per step for the bare access pattern; an
-// L2 persisting set-aside was measured too and made everything 2x slower, so none is used).
+// state evict_last lets the 126 MB L2 keep it resident from one launch to the next (an L2 persisting
+// set-aside was measured too and made everything 2x slower, so none is used).  The streams are
+// evict_normal while the state fits its budget and evict_first beyond (mt_create in mt_api.cu).
 #ifdef MT_NO_L2_HINTS   // A/B builds only (tools/ab.py): every access evict_normal
 __device__ __forceinline__ uint64_t policy_evict_last() {
     uint64_t p;

@@ -99,9 +99,10 @@ struct StepParams {
     // evict_last so that it stays in the 126 MB L2 from one step to the next -- for the FRACTION of its
     // lines (chosen by the hardware's address hash, hence the same lines every step) that fits the
     // handle's L2 budget: protecting more lines than the L2 can hold costs more than no hint at all
-    // (tools/microbench/bigstreams.cu, N = 2^22).  pol_stream (evict_first) is for everything that
-    // passes through once per step: actions, objectives, observations, reward, done.
-    unsigned long long pol_state, pol_stream;
+    // (tools/microbench/bigstreams.cu, N = 2^22).  pol_stream / pol_store are for everything that passes
+    // through once per step (actions, objectives in; observations, reward, done out): evict_normal while the
+    // whole state fits its budget, evict_first beyond (mt_create; measured both ways in round 2).
+    unsigned long long pol_state, pol_stream, pol_store;   // pol_store: the streamed OUTPUTS (observations, reward, done)
 };
 
 __host__ __device__ __forceinline__ uint32_t alive_mask_of(const StepParams &P, uint32_t word) {
@@ -889,7 +890,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     // hiding.  With the queue every warp stays busy until the block's tiles run out.  (One ticket counter
     // for the whole grid was measured earlier: ~37k same-address global atomics per launch serialise in L2;
     // a shared-memory atomic per tile costs nothing.)
-    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
+    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state, pol_store = P.pol_store;
     const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
     auto tile_of = [&](int li) -> int {     // (one contiguous range of tiles per block instead: measured, +2.5 us per step)
         const int t = tile_begin + li * (int)gridDim.x + (int)blockIdx.x;
@@ -1009,8 +1010,8 @@ step_kernel(const __grid_constant__ StepParams P) {
             st_hint(P.total_reward + env, total, pol_keep);
             if (!ep_shift) st_hint(P.counters + env, eplen, pol_keep);
             if (valid) {
-                st_hint(P.reward + env, rew, pol_stream);
-                st_hint(P.done + env, done, pol_stream);
+                st_hint(P.reward + env, rew, pol_store);
+                st_hint(P.done + env, done, pol_store);
                 if (P.joints) {
 #pragma unroll
                     for (int i = 0; i < J * 3; ++i) P.joints[env * (J * 3) + i] = jbuf[i];
@@ -1021,7 +1022,7 @@ step_kernel(const __grid_constant__ StepParams P) {
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, buf_cur, tile_bytes, pol_stream);
+                        bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, buf_cur, tile_bytes, pol_store);
                         bulk_commit();
                     }
                 } else if (valid) {
@@ -1093,7 +1094,7 @@ rollout_kernel(const __grid_constant__ StepParams P) {
     const uint32_t pts = sbase + (uint32_t)(NB * warp) * P.tile_bytes, obuf = pts + P.tile_bytes;
     const uint32_t bar = sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)warp * 8u;
     const uint32_t queue = smem_addr(&queue_next);
-    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state;
+    const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state, pol_store = P.pol_store;
     const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
     auto tile_of = [&](int li) -> int {
         const int t = tile_begin + li * (int)gridDim.x + (int)blockIdx.x;
@@ -1155,15 +1156,15 @@ rollout_kernel(const __grid_constant__ StepParams P) {
 #pragma unroll
                 for (int i = 0; i < J; ++i) sc.g[i] = gn[i];
                 if (valid) {
-                    st_hint(P.reward + env, rew, pol_stream);
-                    st_hint(P.done + env, done, pol_stream);
+                    st_hint(P.reward + env, rew, pol_store);
+                    st_hint(P.done + env, done, pol_store);
                 }
                 if (WOBS) {
                     if (full) {
                         fence_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, obuf, tile_bytes, pol_stream);
+                            bulk_store_hint_s(P.obs + (size_t)env0 * rowlen, obuf, tile_bytes, pol_store);
                             bulk_commit();
                         }
                     } else if (valid) {
