@@ -12,3 +12,5 @@ python tools/parity_soak.py --arm ref --n 16384 --steps 600 > gpurun_out/r2p_soa
 python tools/parity_soak.py --arm ref --n 8192 --steps 300 --float > gpurun_out/r2p_soak2.log 2>&1
 python tools/parity_soak.py --arm ur5 --n 163840 --steps 30 > gpurun_out/r2p_soak3.log 2>&1
 tail -3 gpurun_out/r2p_tests.log; tail -1 gpurun_out/r2p_soak1.log gpurun_out/r2p_soak2.log gpurun_out/r2p_soak3.log; cut -c1-400 gpurun_out/r2p_bench.json
+python tools/run_config.py ref 60 > gpurun_out/r2p_plain4.log 2>&1 && ncu --cache-control none --clock-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:step_kernel -s 30 -c 20 --csv --log-file gpurun_out/r2p_dram_warm.csv python tools/run_config.py ref 60 > /dev/null 2>&1
+tail -3 gpurun_out/r2p_dram_warm.csv
