@@ -100,12 +100,15 @@ class _PinnedBlock:
     only when the last view is gone -- not when the BatchedEnvs that allocated it is collected."""
 
     def __init__(self, nbytes: int, alloc=None, free=None):
-        lib = _lib.load() if alloc is None else None
-        self._free = free if free is not None else lib.mt_host_free
+        if (alloc is None) != (free is None):
+            raise ValueError("pass both `alloc` and `free` (tests) or neither (mt_host_alloc / mt_host_free)")
         ptr = C.c_void_p()
         if alloc is None:
+            lib = _lib.load()
+            self._free = lib.mt_host_free
             _lib.check(lib.mt_host_alloc(C.byref(ptr), max(int(nbytes), 1)))
         else:
+            self._free = free
             ptr = C.c_void_p(alloc(max(int(nbytes), 1)))
         self.ptr = ptr.value
         self._finalizer = weakref.finalize(self, self._free, C.c_void_p(self.ptr))

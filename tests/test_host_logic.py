@@ -67,3 +67,29 @@ def test_stats_allreduce_world2_gloo():
         assert out[r][1] == 2.0               # max over ranks of the per-rank time
     assert mtd.stats_dict(torch.tensor(expect))["env_steps"] == expect[0]
     assert list(mtd.stats_dict(torch.tensor(expect))) == list(STATS_FIELDS)
+
+
+def test_pinned_views_keep_their_allocation_alive():
+    """arrays handed out over page-locked memory must own it -- the block is released when the LAST
+    view goes, not when the wrapper (or the BatchedEnvs that made it) is collected.  Checked here with a fake
+    allocator; the GPU suite repeats it on real pinned memory."""
+    import ctypes as C
+    import gc
+    from manytor_b200.core import PinnedArray
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    freed = []
+    pa = PinnedArray((4, 3), np.float32, lambda n: libc.malloc(n), lambda p: freed.append(p.value))
+    view = pa.array[1:3]
+    ptr = pa.ptr
+    del pa
+    gc.collect()
+    assert freed == []
+    view[:] = 1.0
+    assert float(view.sum()) == 6.0
+    del view
+    gc.collect()
+    assert freed == [ptr]
+    with pytest.raises(ValueError):
+        PinnedArray((2,), np.float32, alloc=lambda n: libc.malloc(n))
