@@ -1,6 +1,7 @@
-// The fused step kernel: one launch = Environment.step for every env of a shard.
+// The fused step kernels: one launch of step_kernel = Environment.step for every env of a shard;
+// one launch of rollout_kernel = n_steps x step(action_sample()) for every env of a shard.
 //
-// Restates, per environment (lane), the reference's
+// Both restate, per environment (lane), the reference's
 //   step          manytor.py:255-260
 //   action        manytor.py:175-213   (25 interpolated poses, ground flag, reward)
 //   fk / dh       manytor.py:35-53, 25-32 (closed form for the reference arm,
@@ -10,12 +11,14 @@
 //   reset         manytor.py:219-241   (auto-reset with on-device objective refresh)
 //
 // Mapping: one persistent block per SM; a warp owns a tile of 32 consecutive envs at a time, one lane
-// per env, and takes its next tile from the block's queue in shared memory.  The tile's objectives (3X fp32 per env, 120 B at X=10) are fetched from HBM by ONE TMA bulk
-// copy into shared memory while the lanes do the kinematics (which need no objectives);
-// observations are written in place over the objectives and leave by ONE TMA bulk store, so the
-// row-major [N][3X] layouts are moved with full-line transactions and no per-lane strided access.
-// All other state is fp32/u32 structure-of-arrays, read and written once per step with coalesced
-// (vector) accesses and prefetched one tile ahead.  Independent fp32 work is packed two lanes per
+// per env, and takes its next tile from the block's queue in shared memory.  The tile's objectives
+// (3X fp32 per env, 120 B at X=10) are fetched from HBM by ONE TMA bulk copy into shared memory while
+// the lanes do the kinematics (which need no objectives); observations leave by ONE TMA bulk store
+// (step_kernel writes them in place over the objectives, rollout_kernel into a second buffer because it
+// keeps the objectives for the next step), so the row-major [N][3X] layouts are moved with full-line
+// transactions and no per-lane strided access.  All other state is fp32/u32 structure-of-arrays, read
+// and written once per step (once per n_steps in rollout_kernel, which keeps it in registers) with
+// coalesced vector accesses, prefetched one tile ahead.  Independent fp32 work is packed two lanes per
 // instruction (FFMA2 / FADD2 / FMUL2).  DESIGN.md section 4 has the measurements behind each choice.
 #pragma once
 #include "../../include/manytor_b200.h"
@@ -37,9 +40,10 @@ constexpr int kTile = 32;
 constexpr int kMaxWarpsRefArm = 28, kMaxWarpsGeneric = 16;
 // Statistics and counters live on the DEVICE, so that a replayed CUDA graph counts its steps and draws
 // fresh actions (the host never sees a replay).  Every warp adds its share to accumulators in shared
-// memory; the last warp of a block flushes them with one global atomic per word (148 per launch and
-// address: every WARP finishing with a global atomic on one address was measured at +3.6 us per launch),
-// and the last block of a launch -- found with a ticket -- bumps the step index and the env-step count.
+// memory; the last warp of a block flushes them with one fire-and-forget global atomic per word (148 per
+// launch and address: every WARP finishing with a global atomic on one address was measured at +3.6 us
+// per launch), and a ticket taken at the START of the launch decides which block advances the step index
+// and the env-step count (launch_ticket below).
 // Control words (StepParams::ctrl, 64-bit each): [0] step index, [1 + slot] launch tickets.
 constexpr int kCtrlStep = 0, kCtrlTicket = 1, kTicketSlots = 31, kCtrlWords = kCtrlTicket + kTicketSlots;
 constexpr int kBlockStats = 6;   // episodes, terminated, reward_sum, length_sum, catches, ground_steps = mt_stats words 1..6
