@@ -465,8 +465,8 @@ extern "C" int mt_get_config(const mt_env *e, mt_config *out) {
 __device__ __forceinline__ void pose_of(const StepParams &P, int arm, const float *g, Frames &f, float *jout) {
     // final pose only: the same code as the step kernel with no interior sub-poses
     switch (arm) {
-        case 0: ref_arm(g, g, 1, 0.f, f, jout); break;
-#define MT_CASE(JJ) case JJ: { StepParams Q = P; Q.substeps = 1; generic_arm<JJ>(Q, g, g, f, jout); } break;
+        case 0: ref_arm<false>(g, g, 1, 0.f, f, jout); break;
+#define MT_CASE(JJ) case JJ: { StepParams Q = P; Q.substeps = 1; generic_arm<JJ, false>(Q, g, g, f, jout); } break;
         MT_CASE(2) MT_CASE(3) MT_CASE(4) MT_CASE(5) MT_CASE(6) MT_CASE(7) MT_CASE(8)
         MT_FOR_EACH_PRESET_ARM(MT_CASE)
 #undef MT_CASE
@@ -704,6 +704,15 @@ static int check_ptr(const void *p, const char *name, bool required) {
     return MT_OK;
 }
 
+// Entries of the per-block sin/cos table for in-kernel (integer-degree) actions (ActionTrig, mt_step.cuh): the whole
+// action range when it is small enough to sit beside the tile buffers, else none (the kernels then evaluate).
+static int trig_table_entries(const mt_env *e) {
+    if (const char *v = std::getenv("MT_ACTION_TABLE"))
+        if (v[0] == '0') return 0;
+    const long long span = (long long)e->cfg.action_high - (long long)e->cfg.action_low;
+    return span >= 1 && span <= 720 ? (int)span : 0;
+}
+
 // Block shape and grid of a persistent launch of `fn` over `tiles` tiles: as many warps as ONE block can have on
 // an SM (they share the block's tile queue), bounded by the kernel's __launch_bounds__ and by shared memory
 // (`per_warp` bytes each); MT_WARPS_PER_BLOCK overrides the target (tuning / A-B runs).  A launch with fewer
@@ -715,7 +724,7 @@ struct LaunchShape {
     size_t smem = 0;
 };
 
-static int plan_launch(mt_env *e, const void *fn, size_t per_warp, long long tiles, LaunchShape &out) {
+static int plan_launch(mt_env *e, const void *fn, size_t per_warp, size_t extra, long long tiles, LaunchShape &out) {
     int max_wpb = 0;
     auto hit = e->block_shape.find(fn);
     if (hit != e->block_shape.end()) {
@@ -726,10 +735,10 @@ static int plan_launch(mt_env *e, const void *fn, size_t per_warp, long long til
             const int v = std::atoi(w);
             if (v >= 1 && v <= max_wpb) max_wpb = v;
         }
-        const size_t smem_cap = 227 * 1024 - 2048;                // per-SM limit minus the per-block reserve
+        const size_t smem_cap = 227 * 1024 - 2048 - extra;        // per-SM limit minus the per-block reserve (and the action table)
         if ((size_t)max_wpb * per_warp > smem_cap) max_wpb = (int)(smem_cap / per_warp);
         if (max_wpb < 1) return fail(MT_ERR_CUDA, "step kernel does not fit on an SM (%zu B of shared memory per warp)", per_warp);
-        const size_t smem_max = (size_t)max_wpb * per_warp;
+        const size_t smem_max = (size_t)max_wpb * per_warp + extra;
         if (smem_max > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, max_wpb * kTile, smem_max));
@@ -745,7 +754,7 @@ static int plan_launch(mt_env *e, const void *fn, size_t per_warp, long long til
         if (occ != e->occupancy.end()) {
             per_sm = occ->second;
         } else {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * kTile, (size_t)wpb * per_warp));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, wpb * kTile, (size_t)wpb * per_warp + extra));
             if (per_sm < 1) per_sm = 1;
             e->occupancy[key] = per_sm;
         }
@@ -754,7 +763,7 @@ static int plan_launch(mt_env *e, const void *fn, size_t per_warp, long long til
     const long long cap = (long long)per_sm * e->num_sms;
     out.wpb = wpb;
     out.grid = (unsigned)(want < cap ? want : cap);
-    out.smem = (size_t)wpb * per_warp;
+    out.smem = (size_t)wpb * per_warp + extra;
     return MT_OK;
 }
 
@@ -808,8 +817,9 @@ static int launch_step(mt_env *e, const float *actions, float *obs, float *rewar
     }
     if (!fn) return fail(MT_ERR_INVALID, "no kernel for arm=%d", e->arm);
     const size_t nb = e->arm == 0 ? StepBuffers<0>::value : StepBuffers<1>::value;   // tile buffers per warp
+    P.trig_span = rnd ? trig_table_entries(e) : 0;
     LaunchShape shape;
-    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + nb * sizeof(uint64_t), t1 - t0, shape)) return rc;
+    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + nb * sizeof(uint64_t), (size_t)P.trig_span * 8, t1 - t0, shape)) return rc;
     if (int rc = launch_pdl(fn, shape, P, st)) return rc;
     e->launches++;
     return MT_OK;
@@ -873,8 +883,9 @@ static int launch_rollout(mt_env *e, int n_steps, float *obs, float *reward, uin
     P.n_steps = n_steps;
     P.launch_envs = e->n * (long long)n_steps;
     const size_t nb = obs ? 2 : 1;                            // objectives (+ observations) per warp, one barrier
+    P.trig_span = trig_table_entries(e);
     LaunchShape shape;
-    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + sizeof(uint64_t), e->n_tiles, shape)) return rc;
+    if (int rc = plan_launch(e, fn, nb * P.tile_bytes + sizeof(uint64_t), (size_t)P.trig_span * 8, e->n_tiles, shape)) return rc;
     if (int rc = launch_pdl(fn, shape, P, st)) return rc;
     e->launches++;
     launched = true;

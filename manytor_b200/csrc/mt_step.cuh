@@ -87,6 +87,7 @@ struct StepParams {
     int32_t n_obj, n_joints, substeps, horizon, flags, obj_sets;
     int32_t action_low;
     uint32_t action_span;
+    int32_t trig_span;         // > 0: in-kernel actions take sin/cos from a per-block table of this many entries (ActionTrig)
     float radius, catch_tol, inv_div;
     int32_t obs_frame, ground_a, ground_b, catch_frame;
     float zero_anchor[3];
@@ -177,11 +178,28 @@ struct CosPair {
     }
 };
 
+// Where the sines / cosines of the joint TARGETS come from.  Actions drawn in-kernel are integer degrees in
+// [action_low, action_low + span): each block fills a table of (sin, cos) per possible value once per launch -- with
+// the very evaluation the kernels would otherwise run per env and step, so a lookup is bit-identical to it -- and the
+// per-step cost of 4..8 sin/cos evaluations becomes as many 64-bit shared-memory loads.  table = 0: evaluate.
+struct ActionTrig {
+    uint32_t table;   // shared-space address of the float2 (sin, cos) entries
+    int32_t low;      // action value of entry 0
+    __device__ __forceinline__ float2 at(float a) const { return lds_f2(table + (uint32_t)(__float2int_rn(a) - low) * 8u); }
+};
+
+template <bool TAB>
 __device__ __forceinline__ void ref_arm(const float *g, const float *a, int substeps, float inv_div, Frames &f,
-                                        float *jout /* 12 floats or nullptr */) {
+                                        float *jout /* 12 floats or nullptr */, ActionTrig trig = ActionTrig{0u, 0}) {
     float2 s01, c01, s23, c23;
-    sincos_deg2(make_float2(a[0], a[1]), s01, c01);
-    sincos_deg2(make_float2(a[2], a[3]), s23, c23);
+    if (TAB && trig.table) {
+        const float2 t0 = trig.at(a[0]), t1 = trig.at(a[1]), t2 = trig.at(a[2]), t3 = trig.at(a[3]);
+        s01 = make_float2(t0.x, t1.x); c01 = make_float2(t0.y, t1.y);
+        s23 = make_float2(t2.x, t3.x); c23 = make_float2(t2.y, t3.y);
+    } else {
+        sincos_deg2(make_float2(a[0], a[1]), s01, c01);
+        sincos_deg2(make_float2(a[2], a[3]), s23, c23);
+    }
     const float s0 = s01.x, c0 = c01.x, s1 = s01.y, c1 = c01.y, s2 = s23.x, c2 = c23.x, s3 = s23.y, c3 = c23.y;
     const float L1 = 24.3f, L2 = 27.0f, H = 4.3f;
     float ez = fmaf(L1, c1, H);
@@ -406,9 +424,9 @@ __device__ __forceinline__ float subpose_zmin(const StepParams &P, float2 *c2, f
 
 // Final pose: 3x4 affine prefix products give the origin of every frame (manytor.py:188-189).
 // Sub-poses: only the z row is propagated, two sub-poses per packed iteration.
-template <int ARM>
+template <int ARM, bool TAB>
 __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g, const float *a, Frames &f,
-                                            float *jout /* J*3 floats or nullptr */) {
+                                            float *jout /* J*3 floats or nullptr */, ActionTrig trig = ActionTrig{0u, 0}) {
     constexpr int J = ArmJoints<ARM>::value;
     constexpr bool kPreset = Preset<ARM>::value;
     const int obs_frame = kPreset ? J - 1 : P.obs_frame, catch_frame = kPreset ? J : P.catch_frame;
@@ -417,7 +435,12 @@ __device__ __forceinline__ void generic_arm(const StepParams &P, const float *g,
     static_for<0, J>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         float si, ci;
-        sincos_deg(a[i], si, ci);
+        if (TAB && trig.table) {
+            const float2 t = trig.at(a[i]);
+            si = t.x; ci = t.y;
+        } else {
+            sincos_deg(a[i], si, ci);
+        }
         const JointConst q = joint_of<ARM, i>(P);
         if (kPreset && q.so == 0.f && q.co == 1.f) {       // no theta offset on this row
             c[i] = ci; s[i] = si;
@@ -790,6 +813,25 @@ __device__ __forceinline__ void settle_step(const StepParams &P, int lane, int e
     __syncwarp();
 }
 
+// Fill the block's ActionTrig table (before the block's first __syncthreads): entry i = the sin / cos the kernel's own
+// evaluation gives for the action value low + i -- the packed evaluation for the reference arm, the scalar one for the
+// generic chain, so that a lookup equals what the same kernel without a table computes, bit for bit.
+template <int ARM>
+__device__ __forceinline__ void fill_action_trig(const StepParams &P, uint32_t table) {
+    for (int i = threadIdx.x; i < P.trig_span; i += blockDim.x) {
+        const float v = (float)(P.action_low + i);
+        float2 sc;
+        if (ARM == 0) {
+            float2 S, C;
+            sincos_deg2(bc2(v), S, C);
+            sc = make_float2(S.x, C.x);
+        } else {
+            sincos_deg(v, sc.x, sc.y);
+        }
+        sts_f2(table + (uint32_t)i * 8u, sc);
+    }
+}
+
 // Device-side bookkeeping of a launch, kept OFF the tail of the launch (a returning atomic or a fence at the
 // end of every block lengthens the launch by its round trip, and the next step cannot start before the whole
 // grid has completed: measured +2 us per step when the ticket sat in the epilogue).
@@ -879,6 +921,7 @@ step_kernel(const __grid_constant__ StepParams P) {
     const uint32_t buf0 = sbase + (uint32_t)(NB * warp) * P.tile_bytes;
     const uint32_t bar0 = sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)(NB * warp) * 8u;
     const uint32_t queue = smem_addr(&queue_next);
+    const ActionTrig trig{RAND && P.trig_span > 0 ? bar0 - (uint32_t)(NB * warp) * 8u + (uint32_t)(NB * wpb) * 8u : 0u, P.action_low};
     // The warp's k-th tile uses buffer / barrier k mod NB, and a barrier's phase parity flips every time it
     // completes, so one counter gives buffer, barrier and parity.
     uint32_t k = 0;
@@ -917,6 +960,7 @@ step_kernel(const __grid_constant__ StepParams P) {
 #pragma unroll
         for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
     }
+    if (RAND && trig.table) fill_action_trig<ARM>(P, trig.table);
     __syncthreads();
     int cur = tile_of(warp);
 #ifdef MT_TRACE
@@ -973,8 +1017,8 @@ step_kernel(const __grid_constant__ StepParams P) {
             Frames f;
             float jbuf[J * 3];
             float *jout = P.joints ? jbuf : nullptr;
-            if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, jout);
-            else generic_arm<ARM>(P, sc.g, sc.a, f, jout);
+            if (ARM == 0) ref_arm<RAND>(sc.g, sc.a, P.substeps, P.inv_div, f, jout, trig);
+            else generic_arm<ARM, RAND>(P, sc.g, sc.a, f, jout, trig);
             const bool neg = f.zmin < 0.0f;                                    // manytor.py:191-192
 
             // 3. next tile's objectives: HBM -> the other buffer by one TMA bulk copy (its previous
@@ -1097,6 +1141,7 @@ rollout_kernel(const __grid_constant__ StepParams P) {
     const uint32_t sbase = smem_addr(smem);
     const uint32_t pts = sbase + (uint32_t)(NB * warp) * P.tile_bytes, obuf = pts + P.tile_bytes;
     const uint32_t bar = sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)warp * 8u;
+    const ActionTrig trig{P.trig_span > 0 ? sbase + (uint32_t)(NB * wpb) * P.tile_bytes + (uint32_t)wpb * 8u : 0u, P.action_low};
     const uint32_t queue = smem_addr(&queue_next);
     const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state, pol_store = P.pol_store;
     const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
@@ -1111,6 +1156,7 @@ rollout_kernel(const __grid_constant__ StepParams P) {
 #pragma unroll
         for (int k = 0; k < kBlockStats; ++k) blk_stat[k] = 0ull;
     }
+    if (trig.table) fill_action_trig<ARM>(P, trig.table);
     __syncthreads();
     int cur = tile_of(warp);
     griddep_launch_dependents();
@@ -1143,8 +1189,8 @@ rollout_kernel(const __grid_constant__ StepParams P) {
             for (int s = 0; s < P.n_steps; ++s) {
                 draw_actions(P, step0 + (unsigned long long)s, P.env_id_base + env32, J, sc.a);
                 Frames f;
-                if (ARM == 0) ref_arm(sc.g, sc.a, P.substeps, P.inv_div, f, nullptr);
-                else generic_arm<ARM>(P, sc.g, sc.a, f, nullptr);
+                if (ARM == 0) ref_arm<true>(sc.g, sc.a, P.substeps, P.inv_div, f, nullptr, trig);
+                else generic_arm<ARM, true>(P, sc.g, sc.a, f, nullptr, trig);
                 const bool neg = f.zmin < 0.0f;
                 if (s == 0) mbar_wait_s(bar, k & 1u);
                 if (WOBS) {                                // the previous step's bulk store must have read the buffer

@@ -436,3 +436,43 @@ def test_policy_loop_example_feeds_fresh_observations(mt):
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:] + res.stdout[-500:]
     assert "graph :" in res.stdout and "episode statistics" in res.stdout
+
+
+@pytest.mark.parametrize("arm_name,x,lo,hi", [("ref", 10, -180, 180), ("ref", 10, -90, 45), ("ref", 7, -1000, 1000),
+                                              ("ur5", 20, -180, 180), ("ur5", 6, -30, 400)])
+def test_action_sincos_table_is_a_pure_memoisation(mt, arm_name, x, lo, hi):
+    """In-kernel actions are integer degrees, so the kernels look the sin / cos of the joint targets up in a per-block
+    table filled by the very evaluation they would otherwise run per env and step (ActionTrig, mt_step.cuh).  With the
+    table (default), without it (MT_ACTION_TABLE=0), and through mt_step on the sampled actions (which always
+    evaluates), every output must be bit-identical -- also for other action ranges and for a range too wide to tabulate."""
+    import torch
+    arm = mt.UR5_ARM if arm_name == "ur5" else mt.REFERENCE_ARM
+    n = 20_000
+    kw = dict(arm=arm, device=0, seed=21, auto_reset=True, horizon=6, action_low=lo, action_high=hi)
+    runs = []
+    for table in ("1", "0", "step"):
+        os.environ["MT_ACTION_TABLE"] = "0" if table == "0" else "1"
+        try:
+            env = mt.BatchedEnvs(n, x, **kw)
+            env.reset()
+            outs = []
+            for t in range(4):
+                if table == "step":
+                    a = env.sample_actions()
+                    assert int(a.min()) >= lo and int(a.max()) < hi
+                    o, r, d = env.step(a)
+                else:
+                    o, r, d = env.rollout_random(1)
+                outs.append((o.clone(), r.clone(), d.clone()))
+            if table != "step":
+                o, r, d = env.rollout_random(9)                    # the multi-step kernel
+                outs.append((o.clone(), r.clone(), d.clone()))
+            runs.append((outs, {k: v.clone() for k, v in env.get_state().items()}, env.stats()))
+        finally:
+            os.environ.pop("MT_ACTION_TABLE", None)
+    for other in runs[1:]:
+        for (o1, r1, d1), (o2, r2, d2) in zip(runs[0][0], other[0]):
+            assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    for key in runs[0][1]:
+        assert torch.equal(runs[0][1][key], runs[1][1][key]), key
+    assert runs[0][2] == runs[1][2]
