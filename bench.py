@@ -460,7 +460,7 @@ def run_gpu(args) -> None:
         a = env.pinned(f"actions{i}", (n, 4), np.float32)
         a[:] = rs.randint(-180, 180, size=(n, 4))
         e2e_acts.append(a)
-    for i in range(5):                                      # untimed: the handle times both host-step variants on its first 4 calls
+    for i in range(8):                                      # untimed: the handle times both host-step variants on its first 6 calls
         env.step_host(e2e_acts[i % e2e_steps])
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()

@@ -172,7 +172,7 @@ int mt_step_host(mt_env *env, const float *actions_host, float *obs_host, float 
                  uint8_t *done_host);
 /* mt_step_host has two implementations with identical results -- chunks staged through device buffers,
  * or one launch reading and writing the pinned host buffers across PCIe itself -- and by default times
- * both on a handle's first four calls and keeps the faster (MT_HOST_ZEROCOPY=0/1 pins it).  Returns 0
+ * both on a handle's first six calls and keeps the faster (MT_HOST_ZEROCOPY=0/1 pins it).  Returns 0
  * staged, 1 zero-copy, 2 still deciding. */
 int mt_host_step_mode(const mt_env *env);
 int mt_host_alloc(void **out, uint64_t bytes);

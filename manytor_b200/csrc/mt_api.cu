@@ -1022,7 +1022,7 @@ extern "C" int mt_host_free(void *p) {
 //              the observations across PCIe, no staging copy, no chunking.
 // Either way the call is bound by the PCIe read-back of the observations (120 of the 125 B per env).  Which one is
 // faster depends on the box: alone on a link staging wins (93 % vs 87 % of the link), with 8 GPUs sharing the host's
-// 93 GB/s zero-copy does (99 % vs 94 %).  So by default the handle TIMES both on its first calls (the call is
+// 93 GB/s zero-copy does (99 % vs 94 %).  So by default the handle TIMES both on its first six calls (the call is
 // synchronous, results are identical) and keeps the faster; MT_HOST_ZEROCOPY=0/1 pins the choice.  The internal
 // streams are ordered after everything submitted earlier to blocking streams (an event on the legacy default stream),
 // not by a device-wide synchronisation.
@@ -1049,9 +1049,10 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
         if (const char *zc = std::getenv("MT_HOST_ZEROCOPY"))
             if (zc[0] == '0' || zc[0] == '1') e->host_mode = zc[0] - '0';
     }
-    // calls 0-1 staged, 2-3 zero-copy (the first of each pair untimed: allocations, first-touch), then the faster one
+    // calls 0-2 staged, 3-5 zero-copy (the first of each triple untimed: allocations, first-touch; the better of the
+    // other two counts), then the faster variant
     const int call = e->host_calls;
-    bool zero_copy = e->host_mode == 1 || (e->host_mode == 2 && (call == 2 || call == 3));
+    bool zero_copy = e->host_mode == 1 || (e->host_mode == 2 && call >= 3);
     if (zero_copy && !(device_visible_host(actions_host) && device_visible_host(obs_host) && device_visible_host(reward_host) &&
                        device_visible_host(done_host))) {
         if (e->host_mode == 1) return fail(MT_ERR_INVALID, "MT_HOST_ZEROCOPY=1 needs buffers from mt_host_alloc (pinned, mapped, 16-byte aligned)");
@@ -1062,8 +1063,8 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
     auto finish = [&]() {
         if (e->host_mode != 2) return;
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
-        if (call == 1 || call == 3) e->host_best[zero_copy ? 1 : 0] = dt;
-        if (++e->host_calls == 4) e->host_mode = e->host_best[1] < 0.98 * e->host_best[0] ? 1 : 0;
+        if (call % 3 != 0 && dt < e->host_best[zero_copy ? 1 : 0]) e->host_best[zero_copy ? 1 : 0] = dt;
+        if (++e->host_calls == 6) e->host_mode = e->host_best[1] < 0.98 * e->host_best[0] ? 1 : 0;
     };
     CU(cudaEventRecord(e->hev[mt_env::kStreams], nullptr));       // everything submitted so far (blocking streams)
     if (zero_copy) {

@@ -317,7 +317,7 @@ def test_zero_copy_host_step_equals_staged(mt):
 
 
 def test_host_step_picks_a_variant_by_itself(mt):
-    """Without MT_HOST_ZEROCOPY the handle tries both implementations on its first four calls and keeps one; every
+    """Without MT_HOST_ZEROCOPY the handle tries both implementations on its first six calls and keeps one; every
     call -- whichever variant served it -- must equal the device step."""
     n = 40_000
     a = mt.BatchedEnvs(n, 10, device=0, seed=3, auto_reset=True, horizon=3)
@@ -325,7 +325,7 @@ def test_host_step_picks_a_variant_by_itself(mt):
     a.reset(); b.reset()
     assert a.host_step_mode == "deciding"
     rng = np.random.RandomState(1)
-    for t in range(7):
+    for t in range(9):
         act = rng.randint(-180, 180, size=(n, 4)).astype(np.float32)
         oa, ra, da = a.step_host(act)
         ob, rb, db = b.step(act)
@@ -333,7 +333,7 @@ def test_host_step_picks_a_variant_by_itself(mt):
         np.testing.assert_array_equal(ra, rb.cpu().numpy())
         np.testing.assert_array_equal(da, db.cpu().numpy())
     assert a.host_step_mode in ("staged", "zero-copy")
-    assert a.stats() == b.stats() and a.step_index == b.step_index == 7
+    assert a.stats() == b.stats() and a.step_index == b.step_index == 9
 
 
 def test_stats_allreduce_c_abi(mt):
