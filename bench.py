@@ -283,6 +283,7 @@ def run_gpu(args) -> None:
     base = rank * n
     env = BatchedEnvs(n, OBJ, device=local, env_id_base=base, horizon=HORIZON, auto_reset=True, seed=SEED)
     env.reset()
+    reducer = mtd.StatsReducer(dev)                   # N > 1: the library's own kernel over NVLink peer memory, else NCCL
     K, W, R = args.steps, max(args.warmup, 3), max(args.repeats, 1)
     stream = torch.cuda.current_stream(dev)
     gen = torch.Generator(device=dev)
@@ -352,8 +353,7 @@ def run_gpu(args) -> None:
         else:
             eager()
         e1.record(stream)
-        st = env.stats_tensor()                       # end-of-rollout statistics ...
-        mtd.allreduce_stats(st)                       # ... one NCCL all-reduce (config 4)
+        st = reducer.reduce(env)                      # end-of-rollout statistics + the one collective (config 4)
         e2.record(stream)
         fence()
         return e0.elapsed_time(e2), e0.elapsed_time(e1), st
@@ -506,8 +506,8 @@ def run_gpu(args) -> None:
                        "burn_in": f"{args.burn_in} + {args.clock_warm_s:.1f} s of in-kernel random-action steps before the first repeat (steady state of the episode process)",
                        "repeats": f"{R} timed regions of exactly K steps each (W warm-up steps before each); value = the median region, best reported beside it",
                        "l2": f"working set {(n * (B + 8 * 4)) / 2**20:.0f} MiB per step > 126 MiB L2 (inputs larger than L2, no flush needed)",
-                       "parallelism": f"env-sharded x{world}, no per-step collective, 1 stats all-reduce (inside the timed region: "
-                                      "a 148-block stats kernel + one ncclAllReduce of 64 B, the only thing that grows with N)"},
+                       "parallelism": f"env-sharded x{world}, no per-step collective, 1 stats all-reduce inside the timed region "
+                                      f"(a stats kernel + the exchange of 64 B, the only thing that grows with N); collective path: {reducer.path}"},
             "repeats": {"n": R, "ms_per_step_all": [t / K for t, _ in reps], "median_ms_per_step": ms_total / K,
                         "best_ms_per_step": best_total / K, "best_value": world * n * K / (best_total * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

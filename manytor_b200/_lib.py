@@ -86,6 +86,8 @@ SIGNATURES = {
     "mt_stats_clear": (C.c_int, [_P, _P]),
     "mt_stats_allreduce": (C.c_int, [C.POINTER(_P), C.c_int32, C.POINTER(MtStats)]),
     "mt_stats_allreduce_comm": (C.c_int, [_P, _P, _P, _P]),
+    "mt_stats_peer_buffer_bytes": (C.c_int64, [C.c_int32]),
+    "mt_stats_allreduce_peers": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     "mt_fk": (C.c_int, [C.POINTER(MtConfig), C.c_int32, _P, _P, C.c_int64, _P]),
     "mt_dh": (C.c_int, [_P, _P, C.c_int64, _P]),
     "mt_joints": (C.c_int, [_P, _P, _P, C.c_int64, _P]),

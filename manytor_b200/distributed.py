@@ -70,6 +70,55 @@ def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     return stats
 
 
+class StatsReducer:
+    """The one collective of a multi-GPU rollout as ONE small kernel of the library over NVLink peer memory
+    (`mt_stats_allreduce_peers`): every rank's 64-byte statistics go straight into every peer's buffer, a flag per
+    peer says when.  torch's symmetric memory only maps the buffers (plumbing).  Where that is unavailable -- a
+    single process, a CPU group, an older torch -- `reduce` falls back to `all_reduce` (NCCL / gloo), and says so
+    in `self.path`."""
+
+    def __init__(self, device=None, group=None, use_peers: bool = True):
+        self.group = group
+        self.path = "local"
+        self._peers = self._buf = self._hdl = None
+        if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        self.path = "all_reduce"
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if not use_peers or device is None or torch.device(device).type != "cuda" or os.environ.get("MT_STATS_PEERS", "1") == "0":
+            return
+        try:
+            import ctypes as C
+            import torch.distributed._symmetric_memory as symm
+            from . import _lib
+            words = int(_lib.load().mt_stats_peer_buffer_bytes(self.world)) // 8
+            self._buf = symm.empty(words, dtype=torch.int64, device=device)
+            self._buf.zero_()
+            self._hdl = symm.rendezvous(self._buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+                raise RuntimeError("symmetric memory returned no peer pointers")
+            self._peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                     # every buffer is zeroed before anyone's first exchange
+            self.path = "peer memory kernel (mt_stats_allreduce_peers over NVLink, buffers mapped by torch symmetric memory)"
+        except Exception as ex:                     # noqa: BLE001 -- any failure here only selects the fallback
+            self._peers = None
+            self.path = f"all_reduce (peer-memory path unavailable: {type(ex).__name__}: {str(ex)[:120]})"
+
+    def reduce(self, env) -> torch.Tensor:
+        """Global sum of `env`'s statistics (MT_STATS_WORDS int64 on its device), asynchronous on the current stream."""
+        if self._peers is None:
+            return allreduce_stats(env.stats_tensor(), self.group)
+        import ctypes as C
+        from . import _lib
+        out = torch.empty((len(STATS_FIELDS),), dtype=torch.int64, device=env.device)
+        stream = C.c_void_p(torch.cuda.current_stream(env.device).cuda_stream)
+        _lib.check(env._lib.mt_stats_allreduce_peers(env._h, C.c_void_p(self._peers.data_ptr()), self.rank, self.world,
+                                                      C.c_void_p(out.data_ptr()), stream))
+        return out
+
+
 def stats_dict(stats: torch.Tensor) -> dict:
     v = stats.detach().cpu().tolist()
     return {k: int(v[i]) for i, k in enumerate(STATS_FIELDS)}

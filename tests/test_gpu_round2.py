@@ -476,3 +476,49 @@ def test_action_sincos_table_is_a_pure_memoisation(mt, arm_name, x, lo, hi):
     for key in runs[0][1]:
         assert torch.equal(runs[0][1][key], runs[1][1][key]), key
     assert runs[0][2] == runs[1][2]
+
+
+def _peer_stats_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import manytor_b200
+    from manytor_b200 import distributed as mtd
+    mtd.init_from_env()
+    torch.cuda.set_device(rank)
+    env = manytor_b200.BatchedEnvs(30_000 + 64 * rank, 10, device=rank, seed=2, auto_reset=True, horizon=5, env_id_base=10 ** 6 * rank)
+    env.reset()
+    red = mtd.StatsReducer(torch.device("cuda", rank))
+    sums = []
+    for it in range(5):                                           # several exchanges: both slot parities, epoch bookkeeping
+        env.rollout_random(7)
+        mine = env.stats_tensor().clone()
+        total = red.reduce(env)
+        ref = mine.clone()
+        dist.all_reduce(ref)                                      # NCCL as the checker
+        torch.cuda.synchronize()
+        sums.append((total.tolist(), ref.tolist()))
+    out[rank] = (red.path, sums)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_peer_memory_stats_allreduce_equals_nccl(mt):
+    """mt_stats_allreduce_peers: the library's own kernel over NVLink peer memory (buffers mapped by torch symmetric
+    memory) must give every rank the same sum as ncclAllReduce, call after call.  Needs >= 2 GPUs."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_peer_stats_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        path, sums = out[r]
+        assert path.startswith("peer memory kernel"), path
+        for total, ref in sums:
+            assert total == ref
+    assert out[0][1] == out[1][1]

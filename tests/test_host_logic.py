@@ -46,6 +46,17 @@ def _worker(rank, world, port, n_total, out):
                          dtype=torch.int64)
     assert stats.numel() == MT_STATS_WORDS
     mtd.allreduce_stats(stats)
+
+    class FakeEnv:                                   # StatsReducer on a CPU group: the all_reduce fallback
+        device = torch.device("cpu")
+
+        def stats_tensor(self):
+            return torch.tensor([count, 1, 0, 0, 0, 0, 0, rank], dtype=torch.int64)
+
+    red = mtd.StatsReducer(device=None)
+    assert red.path == "all_reduce"
+    got = red.reduce(FakeEnv()).tolist()
+    assert got[0] == n_total and got[1] == world and got[7] == sum(range(world))
     t = mtd.max_over_ranks(1.0 + rank)
     out[rank] = (stats.tolist(), t, base, count)
     dist.barrier()
