@@ -220,7 +220,8 @@ int mt_stats_allreduce_comm(mt_env *env, void *nccl_comm, int64_t *stats_dev, vo
  * addresses as seen from this rank.  One small kernel per rank stores this rank's 64 bytes into every
  * peer's buffer, raises a flag there and waits for the peers' flags in its own: ~4 us instead of
  * ~30 us for the NCCL call.  Asynchronous on `stream`; the epoch that keys the flags lives in device
- * memory (graph-replay safe).  Every rank of the group must make the call. */
+ * memory (graph-replay safe).  Every rank of the group must make the call; if a peer never does, the
+ * kernel gives up after ~10 s and writes -1 into every word instead of hanging the GPU. */
 int64_t mt_stats_peer_buffer_bytes(int32_t world);
 int mt_stats_allreduce_peers(mt_env *env, int64_t *const *peers_dev, int32_t rank, int32_t world,
                              int64_t *stats_dev, void *stream);

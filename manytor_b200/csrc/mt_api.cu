@@ -1230,11 +1230,15 @@ extern "C" int mt_stats_device(mt_env *e, int64_t *stats_dev, void *stream) {
 __global__ void stats_exchange_kernel(const long long *local, long long *const *peers, int rank, int world, long long *out) {
     __shared__ long long acc[MT_STATS_WORDS];
     __shared__ long long epoch_s;
+    __shared__ int timed_out;
     const int r = threadIdx.x;
     long long *mine = peers[rank];
     const size_t slot_words = (size_t)2 * world * MT_STATS_WORDS, flag_words = (size_t)2 * world;
     if (r < MT_STATS_WORDS) acc[r] = 0;
-    if (r == 0) epoch_s = ++mine[slot_words + flag_words];
+    if (r == 0) {
+        epoch_s = ++mine[slot_words + flag_words];
+        timed_out = 0;
+    }
     __syncthreads();
     const long long epoch = epoch_s;
     const size_t par = (size_t)(epoch & 1);
@@ -1246,7 +1250,12 @@ __global__ void stats_exchange_kernel(const long long *local, long long *const *
         __threadfence_system();
         *reinterpret_cast<volatile long long *>(peer + slot_words + par * world + rank) = epoch;
         volatile long long *flag = mine + slot_words + par * world + r;
+        const long long t0 = clock64();
         while (*flag != epoch) {
+            if (clock64() - t0 > 20000000000LL) {      // ~10 s: a peer never made the call -- give up instead of hanging the GPU
+                timed_out = 1;
+                break;
+            }
         }
         __threadfence_system();
         const long long *got = mine + (par * world + r) * MT_STATS_WORDS;
@@ -1255,7 +1264,7 @@ __global__ void stats_exchange_kernel(const long long *local, long long *const *
             atomicAdd(reinterpret_cast<unsigned long long *>(&acc[k]), (unsigned long long)reinterpret_cast<const volatile long long *>(got)[k]);
     }
     __syncthreads();
-    if (r < MT_STATS_WORDS) out[r] = acc[r];
+    if (r < MT_STATS_WORDS) out[r] = timed_out ? -1 : acc[r];      // all words -1: the exchange timed out
 }
 
 extern "C" int64_t mt_stats_peer_buffer_bytes(int32_t world) {

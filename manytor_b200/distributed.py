@@ -100,11 +100,17 @@ class StatsReducer:
                 raise RuntimeError("symmetric memory returned no peer pointers")
             self._peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
             torch.cuda.synchronize(device)
-            dist.barrier(group)                     # every buffer is zeroed before anyone's first exchange
             self.path = "peer memory kernel (mt_stats_allreduce_peers over NVLink, buffers mapped by torch symmetric memory)"
         except Exception as ex:                     # noqa: BLE001 -- any failure here only selects the fallback
             self._peers = None
             self.path = f"all_reduce (peer-memory path unavailable: {type(ex).__name__}: {str(ex)[:120]})"
+        # the choice must be the same on every rank (a rank on the fallback would leave the others waiting for its
+        # flag): one MIN over a success bit; this collective is also the barrier after which every buffer is zeroed
+        ok = torch.tensor([1 if self._peers is not None else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0 and self._peers is not None:
+            self._peers = None
+            self.path = "all_reduce (peer-memory path unavailable on another rank)"
 
     def reduce(self, env) -> torch.Tensor:
         """Global sum of `env`'s statistics (MT_STATS_WORDS int64 on its device), asynchronous on the current stream."""
