@@ -28,11 +28,8 @@ t0, t1, sm, tiles = tr[:, 0], tr[:, 1], tr[:, 2], tr[:, 3]
 base = t0.min()
 span = t1.max() - base
 print(f"{len(tr)} warps, {len(np.unique(sm))} SMs, launch span {span/1e3:.2f} us (first warp start -> last warp end)")
-blocks = np.arange(len(tr)) // 4
-per_sm = np.bincount(sm[::4])
-print(f"blocks per SM: min {per_sm[per_sm>0].min()} max {per_sm.max()};  block b on SM (b mod 148)? "
-      f"{np.mean(sm[::4] == (blocks[::4] % 148))*100:.0f}% ; same SM for b and b+148: "
-      f"{np.mean(sm[::4][:-148] == sm[::4][148:])*100:.0f}%")
+per_sm = np.bincount(sm)
+print(f"warps per SM: min {per_sm[per_sm>0].min()} max {per_sm.max()}")
 q = lambda v: " ".join(f"{np.percentile(v, p)/1e3:6.2f}" for p in (0, 10, 50, 90, 100))
 print(f"warp start after launch start (us), p0/10/50/90/100: {q(t0 - base)}")
 print(f"warp end   after launch start (us), p0/10/50/90/100: {q(t1 - base)}")
@@ -48,3 +45,15 @@ spread = [t1[sm == s].max() - t1[sm == s].min() for s in np.unique(sm)]
 print(f"per-SM spread between first and last warp finish: median {np.median(spread)/1e3:.2f} us, max {np.max(spread)/1e3:.2f} us")
 ends = np.array([t1[sm == s].max() - base for s in np.unique(sm)])
 print(f"per-SM finish time: min {ends.min()/1e3:.2f} median {np.median(ends)/1e3:.2f} max {ends.max()/1e3:.2f} us")
+# does the SM that starts late finish late?  (a launch's blocks become resident as the previous launch's blocks exit)
+sms = np.unique(sm)
+starts = np.array([t0[sm == s].min() - base for s in sms])
+print(f"per-SM first warp start: p50 {np.median(starts)/1e3:.2f} p90 {np.percentile(starts,90)/1e3:.2f} max {starts.max()/1e3:.2f} us; "
+      f"correlation(start, finish) over SMs = {np.corrcoef(starts, ends)[0,1]:.2f}")
+order = np.argsort(-ends)[:8]
+print("latest SMs (sm: start -> finish us, tiles done): " +
+      ", ".join(f"{int(sms[i])}: {starts[i]/1e3:.2f} -> {ends[i]/1e3:.2f}, {int(tiles[sm == sms[i]].sum())}" for i in order))
+per_sm_tiles = np.array([tiles[sm == s].sum() for s in sms])
+print(f"tiles per SM: min {per_sm_tiles.min()} median {int(np.median(per_sm_tiles))} max {per_sm_tiles.max()}; "
+      f"busy span (finish - start) per SM: p10 {np.percentile(ends-starts,10)/1e3:.2f} p50 {np.median(ends-starts)/1e3:.2f} "
+      f"p90 {np.percentile(ends-starts,90)/1e3:.2f} max {(ends-starts).max()/1e3:.2f} us")
