@@ -48,7 +48,7 @@ arm = UR5_ARM if args.arm == "ur5" else REFERENCE_ARM
 J = arm.n_joints
 envs = []
 for p, (_, keep) in zip(paths, specs):
-    for k in ("MT_L2_KEEP_MB", "MT_WARPS_PER_BLOCK", "MT_TILE_POOL"):
+    for k in ("MT_L2_KEEP_MB", "MT_WARPS_PER_BLOCK", "MT_TAIL_RANKS", "MT_TAIL_RATE"):
         os.environ.pop(k, None)
     for kv in (keep.split(",") if keep else []):     # "48" = MT_L2_KEEP_MB=48; "K=V" sets any variable
         k, _, v = kv.rpartition("=")

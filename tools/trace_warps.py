@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where does a step launch lose time at its ends?  Needs a -DMT_TRACE build of the library:
   nvcc <build.py flags> -DMT_TRACE -o tools/ab/trace.so manytor_b200/csrc/mt_api.cu
-  python tools/trace_warps.py tools/ab/trace.so [lg_envs]
+  python tools/trace_warps.py tools/ab/trace.so [lg_envs [raw.npy]]
 Prints, for the last of a few hundred back-to-back steps: how blocks were placed on SMs, the spread of
 warp start and finish times, tiles per warp, and the share of warp-time between first start and last
 finish in which a warp slot was already empty."""
@@ -24,6 +24,8 @@ lib = C.CDLL(path)
 buf = np.zeros((8192, 4), dtype=np.uint64)
 assert lib.mt_debug_trace(buf.ctypes.data_as(C.c_void_p)) == 0
 tr = buf[buf[:, 1] > 0].astype(np.int64)
+if len(sys.argv) > 3:                       # raw rows (start ns, end ns, SM, tiles), warp w = block * warps_per_block + warp
+    np.save(sys.argv[3], tr)
 t0, t1, sm, tiles = tr[:, 0], tr[:, 1], tr[:, 2], tr[:, 3]
 base = t0.min()
 span = t1.max() - base
