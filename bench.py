@@ -204,7 +204,7 @@ def config1_latency(steps: int = 1000) -> dict:
     dt = time.perf_counter() - t0
     return {"workload": "configs[0]: Environment(10), 1000 x step(action_sample()), reset on done", "steps": steps,
             "env_steps_per_s": steps / dt, "us_per_step": 1e6 * dt / steps,
-            "note": "each iteration = mt_sample_actions + its read-back, then ONE mt_step_host call (upload, kernel, read-back) through ctypes; launch-latency bound"}
+            "note": "each iteration = action_sample() on the host (np.random, like the reference), then ONE mt_step_host call (upload, kernel, read-back) through ctypes; launch-latency bound"}
 
 
 def run_reference_arm(args) -> None:

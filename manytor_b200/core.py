@@ -153,6 +153,8 @@ class BatchedEnvs:
         self._obs = self._reward = self._done = self._joints = self._actions = None
         self._stream_keepalive = None
         self._pinned = {}
+        self._pinned_ptr = {}                              # id(array) -> address, for the arrays in _pinned (kept alive there)
+        self._host_io = {}                                 # write_obs -> step_host's buffers and their addresses
 
     # -- plumbing -------------------------------------------------------------
     def close(self):
@@ -252,7 +254,8 @@ class BatchedEnvs:
     def pinned(self, name: str, shape, dtype) -> np.ndarray:
         key = (name, tuple(shape), np.dtype(dtype).str)
         if key not in self._pinned:
-            self._pinned[key] = PinnedArray(shape, dtype)
+            pa = self._pinned[key] = PinnedArray(shape, dtype)
+            self._pinned_ptr[id(pa.array)] = pa.ptr
         return self._pinned[key].array
 
     def step_host(self, actions_host: np.ndarray, write_obs: bool = True):
@@ -262,16 +265,20 @@ class BatchedEnvs:
         input is staged through `pinned('actions', ...)`.  The returned arrays are views of
         page-locked buffers that the NEXT step_host overwrites; they stay valid (they own the
         allocation) even after this object is gone."""
-        if any(actions_host is pa.array for pa in self._pinned.values()):
-            act = actions_host                             # already one of this object's page-locked buffers
-        else:
+        io = self._host_io.get(write_obs)
+        if io is None:                                     # buffers and addresses once: a batch of one is pure latency
             act = self.pinned("actions", (self.n, self.j), np.float32)
+            obs = self.pinned("obs", (self.n, 3 * self.x), np.float32) if write_obs else None
+            rew = self.pinned("reward", (self.n,), np.float32)
+            done = self.pinned("done", (self.n,), np.uint8)
+            addr = lambda a: self._pinned_ptr[id(a)] if a is not None else None
+            io = self._host_io[write_obs] = (act, addr(act), obs, addr(obs), rew, addr(rew), done, addr(done))
+        act, act_ptr, obs, obs_ptr, rew, rew_ptr, done, done_ptr = io
+        own = self._pinned_ptr.get(id(actions_host))       # already one of this object's page-locked buffers?
+        if own is None:
             np.copyto(act, np.asarray(actions_host, dtype=np.float32).reshape(self.n, self.j))
-        obs = self.pinned("obs", (self.n, 3 * self.x), np.float32) if write_obs else None
-        rew = self.pinned("reward", (self.n,), np.float32)
-        done = self.pinned("done", (self.n,), np.uint8)
-        _lib.check(self._lib.mt_step_host(self._h, act.ctypes.data, obs.ctypes.data if write_obs else None,
-                                          rew.ctypes.data, done.ctypes.data))
+            own = act_ptr
+        _lib.check(self._lib.mt_step_host(self._h, own, obs_ptr, rew_ptr, done_ptr))
         return obs, rew, done
 
     @property

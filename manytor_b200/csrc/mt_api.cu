@@ -1066,15 +1066,16 @@ extern "C" int mt_step_host(mt_env *e, const float *actions_host, float *obs_hos
         if (call % 3 != 0 && dt < e->host_best[zero_copy ? 1 : 0]) e->host_best[zero_copy ? 1 : 0] = dt;
         if (++e->host_calls == 6) e->host_mode = e->host_best[1] < 0.98 * e->host_best[0] ? 1 : 0;
     };
-    CU(cudaEventRecord(e->hev[mt_env::kStreams], nullptr));       // everything submitted so far (blocking streams)
     if (zero_copy) {
-        CU(cudaStreamWaitEvent(e->hs[0], e->hev[mt_env::kStreams], 0));
-        if (int rc = launch_step(e, actions_host, obs_host, reward_host, done_host, nullptr, false, 0, e->n_tiles, e->hs[0]))
+        // one launch on the legacy stream: ordered after everything submitted so far on blocking streams, like the
+        // event fence of the staged variant below, without the two extra calls (a batch of one env is pure latency)
+        if (int rc = launch_step(e, actions_host, obs_host, reward_host, done_host, nullptr, false, 0, e->n_tiles, nullptr))
             return rc;
-        CU(cudaStreamSynchronize(e->hs[0]));
+        CU(cudaStreamSynchronize(nullptr));
         finish();
         return MT_OK;
     }
+    CU(cudaEventRecord(e->hev[mt_env::kStreams], nullptr));       // everything submitted so far (blocking streams)
     if (!e->h_actions) {
         CU(cudaMalloc((void **)&e->h_actions, (size_t)e->n_pad * J * 4));
         CU(cudaMalloc((void **)&e->h_obs, (size_t)e->n_pad * R * 4));

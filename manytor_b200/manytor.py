@@ -192,6 +192,13 @@ class _TrajectoryLog:
         return self.rows if len(self.pairs) else self.rows[0]                  # manytor.py:135: a (3,) vector before the first step
 
 
+def _host_action_sample(cfg, n_envs):
+    """[[np.random.randint(low, high) for _ in range(J)] for each env] -- manytor.py:215-217 and :111-113; one
+    vectorised call consumes the legacy np.random stream exactly like the reference's scalar calls."""
+    a = np.random.randint(int(cfg.action_low), int(cfg.action_high), size=(n_envs, int(cfg.n_joints)))
+    return [[int(v) for v in row] for row in a]
+
+
 class _EnvView:
     """``multienv.environment[i]``: one env of the batch with the reference's per-env surface
     (manytor.py:125-260; test_multi.py:32 reads ``total_reward``).  Attribute reads copy that env's
@@ -247,8 +254,8 @@ class _EnvView:
         return not bool(self.alives.any())
 
     def action_sample(self):
-        """manytor.py:215-217."""
-        return [int(v) for v in self._owner._envs.sample_actions().cpu().numpy()[self.id]]
+        """manytor.py:215-217: J draws from the process-global np.random stream, like the reference."""
+        return _host_action_sample(self._owner._envs.cfg, 1)[0]
 
     def reset(self, returnable=False):
         """manytor.py:219-253 for this env only."""
@@ -383,9 +390,12 @@ class Multienv:
                 bool(d) if self._horizon > 0 else bool(d & 1))
 
     def action_sample(self):
-        """manytor.py:111-113: per env J integers in [-180, 180)."""
-        a = self._envs.sample_actions().cpu().numpy().astype(np.int64)
-        return [list(r) for r in a] if self.as_lists else a
+        """manytor.py:111-113: per env J integers in [-180, 180).  In list mode they come from the process-global
+        np.random stream in the reference's order (env 0's J draws, then env 1's, ...); in array mode from the
+        device sampler (`mt_sample_actions`, the stream `rollout_random` uses), read back as an (N, J) int64 array."""
+        if self.as_lists:
+            return _host_action_sample(self._envs.cfg, self.env_number)
+        return self._envs.sample_actions().cpu().numpy().astype(np.int64)
 
     def step(self, action):
         """manytor.py:115-122 -> (obs2, reward, done) per env."""
@@ -485,8 +495,9 @@ class Environment:
         return not bool(self.alives.any())
 
     def action_sample(self):
-        """manytor.py:215-217."""
-        return [int(v) for v in self._envs.sample_actions().cpu().numpy()[0]]
+        """manytor.py:215-217: J draws of np.random.randint(-180, 180) from the process-global stream, so a seeded
+        caller sees the reference's actions (no device round trip: a batch of one is pure latency)."""
+        return _host_action_sample(self._envs.cfg, 1)[0]
 
     def reset(self, returnable=False):
         """manytor.py:219-253."""

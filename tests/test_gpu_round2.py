@@ -213,6 +213,30 @@ def test_envview_is_a_real_environment(mt):
     assert 2 not in me.render_envs
 
 
+def test_action_sample_is_the_reference_stream(mt):
+    """manytor.py:215-217, 111-113: action_sample() draws np.random.randint(-180, 180) per joint from the
+    process-global stream, env after env -- a caller that seeds np.random gets the reference's actions."""
+    import manytor_b200.manytor as tor
+    from oracle import action_sample_reference_stream
+    want = lambda k: [[int(v) for v in action_sample_reference_stream()] for _ in range(k)]
+    env = tor.Environment(10)
+    env.reset()
+    np.random.seed(11)
+    got = [env.action_sample() for _ in range(5)]
+    np.random.seed(11)
+    assert got == want(5) and all(type(v) is int for v in got[0])
+    me = tor.Multienv((2, 3), 5)
+    me.reset()
+    np.random.seed(12)
+    got = me.action_sample() + [me.environment[4].action_sample()]
+    np.random.seed(12)
+    assert got == want(7)
+    arr = tor.Multienv((2, 3), 5, as_lists=False)                          # array mode: the device sampler
+    arr.reset()
+    a = arr.action_sample()
+    assert a.shape == (6, 4) and a.dtype == np.int64 and a.min() >= -180 and a.max() < 180
+
+
 def test_pinned_views_outlive_their_env(mt):
     """ADVICE: step_host() returns views of page-locked buffers; they must stay valid after the env that
     allocated them is gone (the views keep the allocation alive)."""
