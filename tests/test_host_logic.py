@@ -104,3 +104,21 @@ def test_pinned_views_keep_their_allocation_alive():
     assert freed == [ptr]
     with pytest.raises(ValueError):
         PinnedArray((2,), np.float32, alloc=lambda n: libc.malloc(n))
+
+
+def test_host_action_sample_is_the_reference_stream():
+    """manytor.py:215-217 / 111-113: the drop-in's action_sample() is J x np.random.randint(low, high) per env from
+    the process-global stream, env after env; one vectorised call must consume that stream like the scalar calls."""
+    import manytor_b200
+    from manytor_b200.core import make_config
+    from manytor_b200.manytor import _host_action_sample
+    from oracle import action_sample_reference_stream
+    cfg = make_config(6, 5, manytor_b200.REFERENCE_ARM, 0)
+    np.random.seed(3)
+    got = _host_action_sample(cfg, 6) + _host_action_sample(cfg, 1)
+    np.random.seed(3)
+    want = [[int(v) for v in action_sample_reference_stream()] for _ in range(7)]
+    assert got == want and all(type(v) is int and -180 <= v < 180 for row in got for v in row)
+    ur5 = make_config(2, 20, manytor_b200.UR5_ARM, 0, action_low=-90, action_high=91)
+    a = _host_action_sample(ur5, 2)
+    assert len(a) == 2 and len(a[0]) == 6 and all(-90 <= v <= 90 for row in a for v in row)
