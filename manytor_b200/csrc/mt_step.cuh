@@ -936,7 +936,12 @@ step_kernel(const __grid_constant__ StepParams P) {
     // 50 us, so for the second half of every launch the SM ran with ever fewer warps and ever less latency
     // hiding.  With the queue every warp stays busy until the block's tiles run out.  (One ticket counter
     // for the whole grid was measured earlier: ~37k same-address global atomics per launch serialise in L2;
-    // a shared-memory atomic per tile costs nothing.)
+    // a shared-memory atomic per tile costs nothing.)  What is left is BETWEEN the SMs: a few of them, not the
+    // same ones every launch, need up to 12 % longer for their 221 tiles (profiles/r2_warp_trace.txt).  A pool of
+    // the launch's last tiles drawn from a global counter -- the draw issued before the kinematics of the tile
+    // in hand and read after them, or two tiles ahead -- and a static relief of the highest-numbered blocks
+    // were built and measured slower or within the noise (profiles/r2_ab_tile_pool.txt, r2_ab_pool_two_ahead.txt,
+    // r2_ab_tail_relief.txt): a second scalar-load site and one more live register cost this kernel 3.6 us.
     const uint64_t pol_stream = P.pol_stream, pol_keep = P.pol_state, pol_store = P.pol_store;
     const int tile_begin = (int)P.tile_begin, tile_end = (int)P.tile_end, n_envs = (int)P.n;
     auto tile_of = [&](int li) -> int {     // (one contiguous range of tiles per block instead: measured, +2.5 us per step)
